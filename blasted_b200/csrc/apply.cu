@@ -1,0 +1,252 @@
+/** \file apply.cu
+ * \brief Asynchronous (block-)triangular solves, SGS sweeps, relaxation and Jacobi application
+ * (K5, K6, K7, K8) as one family of row-sweep kernels.
+ *
+ * Replaces, from the reference:
+ *   scalar_unit_lower_triangular / scalar_upper_triangular   src/kernels/kernels_ilu_apply.hpp:15-42
+ *   block_unit_lower_triangular / block_upper_triangular     kernels_ilu_apply.hpp:54-94
+ *   scalar_fgs / scalar_bgs / block_fgs / block_bgs          src/kernels/kernels_sgs.hpp:17-76
+ *   scalar_relax / block_relax_kernel                        src/kernels/kernels_relaxation.hpp:17-54
+ *   and the sweep loops around them                          src/solverops_ilu0.cpp:99-141,274-314;
+ *                                                            src/solverops_sgs.cpp:62-115,156-202;
+ *                                                            src/solverops_levels_{ilu0,sgs}.cpp
+ *
+ * Every kernel computes, for each (block-)row i of a range,
+ *     x_i <- f( rhs_i , sum_{j in part(i)} V_ij x_j )
+ * with ONE final store of x_i; x_j are relaxed L2 loads that may see old or new values (chaotic
+ * iteration).  CTAs are mapped to rows ascending for lower/forward sweeps and descending for
+ * upper/backward sweeps so that the hardware's in-order CTA dispatch gives the Gauss-Seidel-like
+ * propagation of the reference's ascending / descending `omp for` loops.  The same kernels, launched
+ * per level on an explicit row list, perform the exact level-scheduled substitutions.
+ *
+ * Mapping: scalar - LPR lanes per row + shuffle reduction; block - bs lanes per block-row, lane r
+ * owns row r of every block (column-major: each block column is one contiguous bs*8-byte read of
+ * the group), x_j is a broadcast load, the bs outputs are one contiguous store.
+ * HBM-bound: one L+U pair streams the factor once: (8 b^2 + 4) nnzb + 12 N + 48 b N bytes.
+ */
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ double ld_iter(const double *p) { return __ldcg(p); }
+
+struct TriDev {
+	const int *browptr, *bcolind, *diagind;
+	const double *vals, *dinv, *rhs, *rscale, *xsrc;
+	double *x;
+	const int *rows;
+	int row_begin, row_end;
+	int descending;
+};
+
+template <int KIND>
+__device__ __forceinline__ void part_range(const int s, const int d, const int e, int& js, int& je)
+{
+	if(KIND == TRI_ILU_LOWER || KIND == TRI_SGS_FWD) { js = s; je = d; }
+	else if(KIND == TRI_ILU_UPPER || KIND == TRI_SGS_BWD) { js = d+1; je = e; }
+	else { js = s; je = e; }
+}
+
+template <int LPR, int KIND>
+__global__ void __launch_bounds__(256)
+tri_scalar_kernel(const TriDev a)
+{
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	const long long t = tid / LPR;
+	const int lane = (int)(tid % LPR);
+	const int nrows = a.row_end - a.row_begin;
+	const bool valid = t < nrows;
+	int row = 0, d = 0;
+	double sum = 0;
+	if(valid) {
+		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
+		row = a.rows ? __ldg(a.rows + idx) : idx;
+		const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+		d = __ldg(a.diagind + row);
+		int js, je;
+		part_range<KIND>(s, d, e, js, je);
+		for(int j = js + lane; j < je; j += LPR) {
+			if(KIND == TRI_RELAX && j == d) continue;
+			sum = fma(__ldg(a.vals + j), ld_iter(a.xsrc + __ldg(a.bcolind + j)), sum);
+		}
+	}
+#pragma unroll
+	for(int off = LPR/2; off > 0; off >>= 1)
+		sum += __shfl_down_sync(0xffffffffu, sum, off, LPR);
+	if(valid && lane == 0) {
+		double rhs = __ldg(a.rhs + row);
+		if(a.rscale) rhs *= __ldg(a.rscale + row);
+		double out;
+		if(KIND == TRI_ILU_LOWER) out = rhs - sum;
+		else if(KIND == TRI_ILU_UPPER) out = (1.0/__ldg(a.vals + d)) * (rhs - sum);
+		else if(KIND == TRI_SGS_FWD || KIND == TRI_RELAX) out = __ldg(a.dinv + row) * (rhs - sum);
+		else out = rhs - __ldg(a.dinv + row)*sum;       // TRI_SGS_BWD
+		a.x[row] = out;
+	}
+}
+
+template <int BS, int KIND>
+__global__ void __launch_bounds__(256)
+tri_block_kernel(const TriDev a)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long t = warp*GPW + g;
+	const int nrows = a.row_end - a.row_begin;
+	const bool valid = (g < GPW) && (t < nrows);
+	int row = 0, d = 0;
+	double acc = 0;
+	if(valid) {
+		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
+		row = a.rows ? __ldg(a.rows + idx) : idx;
+		const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+		d = __ldg(a.diagind + row);
+		int js, je;
+		part_range<KIND>(s, d, e, js, je);
+#pragma unroll 2
+		for(int jj = js; jj < je; jj++) {
+			if(KIND == TRI_RELAX && jj == d) continue;
+			const int col = __ldg(a.bcolind + jj);
+			const double *blk = a.vals + (size_t)jj*BS2 + r;
+			const double *xs = a.xsrc + (size_t)col*BS;
+			double av[BS], xv[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++) av[c] = __ldg(blk + c*BS);
+#pragma unroll
+			for(int c = 0; c < BS; c++) xv[c] = ld_iter(xs + c);
+#pragma unroll
+			for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+		}
+	}
+	double rhs = 0;
+	if(valid) {
+		rhs = __ldg(a.rhs + (size_t)row*BS + r);
+		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
+	}
+	double out;
+	if(KIND == TRI_ILU_LOWER) out = rhs - acc;
+	else {
+		// multiply a bs-vector held one entry per lane by a bs x bs block: t_c via shuffles
+		const double tv = (KIND == TRI_SGS_BWD) ? acc : rhs - acc;
+		const double *dblk = nullptr;
+		if(valid)
+			dblk = (KIND == TRI_ILU_UPPER) ? a.vals + (size_t)d*BS2 + r     // pre-inverted U_ii
+			                               : a.dinv + (size_t)row*BS2 + r;  // D_i^-1 of A
+		double prod = 0;
+#pragma unroll
+		for(int c = 0; c < BS; c++) {
+			const double tc = __shfl_sync(0xffffffffu, tv, g*BS + c);
+			if(valid) prod = fma(__ldg(dblk + c*BS), tc, prod);
+		}
+		out = (KIND == TRI_SGS_BWD) ? rhs - prod : prod;
+	}
+	if(valid) a.x[(size_t)row*BS + r] = out;
+}
+
+template <int KIND>
+static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cudaStream_t st)
+{
+	const long long nrows = d.row_end - d.row_begin;
+	if(nrows <= 0) return;
+	if(A.bs == 1) {
+#define B200_TRI_CASE(L)                                                           \
+		{                                                                          \
+			const int grid = div_up(nrows*L, 256);                                 \
+			tri_scalar_kernel<L,KIND><<<grid, 256, 0, st>>>(d);                    \
+		}
+		if(avg_part <= 2.5) B200_TRI_CASE(2)
+		else if(avg_part <= 5) B200_TRI_CASE(4)
+		else if(avg_part <= 10) B200_TRI_CASE(8)
+		else if(avg_part <= 20) B200_TRI_CASE(16)
+		else B200_TRI_CASE(32)
+#undef B200_TRI_CASE
+	}
+	else if(A.bs == 4) {
+		const long long nwarps = (nrows + 7)/8;
+		tri_block_kernel<4,KIND><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
+	}
+	else if(A.bs == 5) {
+		const long long nwarps = (nrows + 5)/6;
+		tri_block_kernel<5,KIND><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
+	}
+	else throw Error("triangular sweep: unsupported block size " + std::to_string(A.bs));
+	B200_LAUNCHED();
+}
+
+void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t st)
+{
+	TriDev d;
+	d.browptr = A.browptr; d.bcolind = A.bcolind; d.diagind = A.diagind;
+	d.vals = a.vals; d.dinv = a.dinv; d.rhs = a.rhs; d.rscale = a.rscale;
+	d.xsrc = a.xsrc ? a.xsrc : a.x; d.x = a.x; d.rows = a.rows;
+	d.row_begin = a.row_begin; d.row_end = a.row_end; d.descending = a.descending ? 1 : 0;
+	const double half = 0.5*(A.avg_row_len - 1.0);
+	switch(kind) {
+	case TRI_ILU_LOWER: launch_kind<TRI_ILU_LOWER>(A, d, half, st); break;
+	case TRI_ILU_UPPER: launch_kind<TRI_ILU_UPPER>(A, d, half, st); break;
+	case TRI_SGS_FWD: launch_kind<TRI_SGS_FWD>(A, d, half, st); break;
+	case TRI_SGS_BWD: launch_kind<TRI_SGS_BWD>(A, d, half, st); break;
+	case TRI_RELAX: launch_kind<TRI_RELAX>(A, d, A.avg_row_len, st); break;
+	}
+}
+
+// ------------------------------------------------------------------ Jacobi application
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+jacobi_apply_kernel(const int nbrows, const double *__restrict__ dinv, const double *__restrict__ rr,
+                    double *__restrict__ z)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= (long long)nbrows*BS) return;
+	const long long row = i / BS;
+	const int r = (int)(i - row*BS);
+	double s = 0;
+#pragma unroll
+	for(int c = 0; c < BS; c++)
+		s = fma(__ldg(dinv + row*BS*BS + c*BS + r), __ldg(rr + row*BS + c), s);
+	z[i] = s;
+}
+
+void launch_jacobi_apply(const Mat& A, const double *dinv, const double *r, double *z, cudaStream_t st)
+{
+	const long long n = (long long)A.nbrows*A.bs;
+	if(n == 0) return;
+	const int grid = div_up(n, 256);
+	switch(A.bs) {
+	case 1: jacobi_apply_kernel<1><<<grid,256,0,st>>>(A.nbrows, dinv, r, z); break;
+	case 4: jacobi_apply_kernel<4><<<grid,256,0,st>>>(A.nbrows, dinv, r, z); break;
+	case 5: jacobi_apply_kernel<5><<<grid,256,0,st>>>(A.nbrows, dinv, r, z); break;
+	default: throw Error("Jacobi: unsupported block size");
+	}
+	B200_LAUNCHED();
+}
+
+// ------------------------------------------------------------------ small vector kernels
+
+__global__ void vec_scale_copy_kernel(const long long n, const double *__restrict__ scale,
+                                      const double *in, double *out)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) out[i] = scale ? scale[i]*in[i] : in[i];
+}
+
+void launch_vec_scale_copy(long long n, const double *scale, const double *in, double *out,
+                           cudaStream_t st)
+{
+	if(n == 0) return;
+	vec_scale_copy_kernel<<<div_up(n,256),256,0,st>>>(n, scale, in, out);
+	B200_LAUNCHED();
+}
+
+void launch_vec_fill(long long n, double v, double *out, cudaStream_t st)
+{
+	if(n == 0) return;
+	if(v == 0.0) { B200_CUDA(cudaMemsetAsync(out, 0, n*sizeof(double), st)); return; }
+	throw Error("vec_fill: only zero supported");
+}
+
+}  // namespace b200

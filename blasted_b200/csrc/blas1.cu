@@ -1,0 +1,140 @@
+/** \file blas1.cu
+ * \brief Vector kernels of the Krylov test drivers (K11): axpby, axpbypcz, fused multi-dot.
+ *
+ * Replaces the OpenMP loops axpby / axpbypcz / dot / vecassign of tests/solvers.cpp:20-60 of the
+ * reference.  Dots are fused (several pairs per pass, one deterministic two-stage reduction) and
+ * their results stay on the device until the driver needs them on the host.
+ */
+#include "common.cuh"
+
+namespace b200 {
+
+__global__ void axpby_kernel(const long long n, const double p, double *z, const double q,
+                             const double *x)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) z[i] = p*z[i] + q*x[i];
+}
+
+__global__ void axpbypcz_kernel(const long long n, const double p, double *z, const double q,
+                                const double *x, const double r, const double *y)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) z[i] = p*z[i] + q*x[i] + r*y[i];
+}
+
+void launch_axpby(long long n, double p, double *z, double q, const double *x, cudaStream_t st)
+{
+	if(n == 0) return;
+	axpby_kernel<<<div_up(n,256),256,0,st>>>(n, p, z, q, x);
+	B200_LAUNCHED();
+}
+
+void launch_axpbypcz(long long n, double p, double *z, double q, const double *x, double r,
+                     const double *y, cudaStream_t st)
+{
+	if(n == 0) return;
+	axpbypcz_kernel<<<div_up(n,256),256,0,st>>>(n, p, z, q, x, r, y);
+	B200_LAUNCHED();
+}
+
+struct DotPtrs { const double *a[MAX_DOTS]; const double *b[MAX_DOTS]; };
+
+template <int ND>
+__global__ void __launch_bounds__(256)
+multi_dot_stage1(const long long n, const DotPtrs p, double *__restrict__ partial)
+{
+	double acc[ND];
+#pragma unroll
+	for(int d = 0; d < ND; d++) acc[d] = 0;
+	for(long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n;
+	    i += (long long)gridDim.x*blockDim.x)
+	{
+#pragma unroll
+		for(int d = 0; d < ND; d++) acc[d] = fma(p.a[d][i], p.b[d][i], acc[d]);
+	}
+	__shared__ double sm[ND][8];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+	for(int d = 0; d < ND; d++) {
+		double v = acc[d];
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+		if(lane == 0) sm[d][w] = v;
+	}
+	__syncthreads();
+	if(threadIdx.x < ND) {
+		double t = 0;
+		for(int i = 0; i < 8; i++) t += sm[threadIdx.x][i];
+		partial[threadIdx.x*DOT_BLOCKS + blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+multi_dot_stage2(const int nd, const int nblocks, const double *__restrict__ partial,
+                 double *__restrict__ out)
+{
+	__shared__ double sm[8];
+	for(int d = 0; d < nd; d++) {
+		double v = 0;
+		for(int i = threadIdx.x; i < nblocks; i += blockDim.x) v += partial[d*DOT_BLOCKS + i];
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+		if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			double t = 0;
+			for(int i = 0; i < 8; i++) t += sm[i];
+			out[d] = t;
+		}
+		__syncthreads();
+	}
+}
+
+void launch_multi_dot(long long n, int nd, const double *const *a, const double *const *b,
+                      double *d_partial, double *d_out, cudaStream_t st)
+{
+	if(nd < 1 || nd > MAX_DOTS) throw Error("multi_dot: bad count");
+	DotPtrs p;
+	for(int d = 0; d < MAX_DOTS; d++) { p.a[d] = a[d < nd ? d : 0]; p.b[d] = b[d < nd ? d : 0]; }
+	const int grid = (int)std::max<long long>(1, std::min<long long>(DOT_BLOCKS, div_up(n, 256)));
+	switch(nd) {
+	case 1: multi_dot_stage1<1><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 2: multi_dot_stage1<2><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 3: multi_dot_stage1<3><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 4: multi_dot_stage1<4><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 5: multi_dot_stage1<5><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 6: multi_dot_stage1<6><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 7: multi_dot_stage1<7><<<grid,256,0,st>>>(n, p, d_partial); break;
+	default: multi_dot_stage1<8><<<grid,256,0,st>>>(n, p, d_partial); break;
+	}
+	B200_LAUNCHED();
+	multi_dot_stage2<<<1,256,0,st>>>(nd, grid, d_partial, d_out);
+	B200_LAUNCHED();
+}
+
+struct AxpyPtrs { const double *v[32]; };
+
+__global__ void __launch_bounds__(256)
+multi_axpy_kernel(const long long n, const int nv, const AxpyPtrs p, const double *__restrict__ coef,
+                  double *y)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double s = y[i];
+	for(int l = 0; l < nv; l++) s = fma(__ldg(coef + l), p.v[l][i], s);
+	y[i] = s;
+}
+
+void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef, double *y,
+                       cudaStream_t st)
+{
+	if(n == 0 || nv == 0) return;
+	if(nv > 32) throw Error("multi_axpy: too many vectors");
+	AxpyPtrs p;
+	for(int l = 0; l < 32; l++) p.v[l] = v[l < nv ? l : 0];
+	multi_axpy_kernel<<<div_up(n,256),256,0,st>>>(n, nv, p, d_coef, y);
+	B200_LAUNCHED();
+}
+
+}  // namespace b200

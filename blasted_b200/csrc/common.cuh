@@ -1,0 +1,217 @@
+/** \file common.cuh
+ * \brief Internal definitions shared by the CUDA translation units of libblasted_b200.so.
+ *
+ * Device storage (the re-design of include/device_container.hpp, srmatrixdefs.hpp of the reference):
+ * CSR/BSR arrays resident in HBM, int32 indices, fp64 values, blocks always COLUMN-major on the
+ * device (row-major input is transposed at the boundary), bs=4 blocks therefore 128-byte aligned.
+ */
+#ifndef B200_COMMON_CUH
+#define B200_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <stdexcept>
+#include <vector>
+#include <atomic>
+
+#include "../../include/blasted_b200.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------- errors
+
+void set_error(const std::string& msg);
+
+struct Error : public std::runtime_error {
+	explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define B200_CUDA(call)                                                                      \
+	do {                                                                                     \
+		cudaError_t e__ = (call);                                                            \
+		if(e__ != cudaSuccess)                                                               \
+			throw b200::Error(std::string(#call) + " failed: " + cudaGetErrorString(e__) +   \
+			                  " (" __FILE__ ":" + std::to_string(__LINE__) + ")");            \
+	} while(0)
+
+extern std::atomic<long long> g_launches;
+
+/// Call after every kernel launch: counts it and surfaces launch-configuration errors
+#define B200_LAUNCHED()                                                                      \
+	do {                                                                                     \
+		b200::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+		B200_CUDA(cudaGetLastError());                                                       \
+	} while(0)
+
+// ---------------------------------------------------------------- device buffers
+
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	DevBuf() {}
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	~DevBuf() { release(); }
+	void release() { if(p) cudaFree(p); p = nullptr; n = 0; }
+	void alloc(size_t count) {
+		if(count == n && p) return;
+		release();
+		if(count == 0) return;
+		B200_CUDA(cudaMalloc((void**)&p, count*sizeof(T)));
+		n = count;
+	}
+	operator T*() const { return p; }
+};
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1)/b); }
+
+// ---------------------------------------------------------------- the matrix
+
+/// Device-resident sparse (block-)row matrix.  Blocks are column-major on the device.
+struct Mat {
+	int nbrows = 0;
+	int bs = 1;
+	int blockstorage = B200_COLMAJOR;     ///< layout of the CALLER's blocks (for copy-in/out)
+	long long nnzb = 0;
+	DevBuf<int> browptr, bcolind, diagind, browind;   ///< browind[jj] = block-row of entry jj
+	DevBuf<double> vals;
+	bool has_diag = false;                ///< every row stores its diagonal (block)
+	int max_row_len = 0;
+	double avg_row_len = 0;
+	cudaStream_t stream = 0;
+	mutable DevBuf<double> hx, hy, hz;    ///< staging for the *_host entry points
+
+	int dim() const { return nbrows*bs; }
+};
+
+// ---------------------------------------------------------------- kernels' host launchers
+// (defined in the .cu files; every launcher is asynchronous on `st`)
+
+// spmv.cu
+void launch_spmv(const Mat& A, const double *x, double *y, cudaStream_t st);
+void launch_gemv3(const Mat& A, double a, const double *x, double b, const double *y, double *z,
+                  cudaStream_t st);
+
+// storage.cu
+void transpose_blocks(int bs, long long nblocks, const double *in, double *out, cudaStream_t st);
+void build_browind(const Mat& A, cudaStream_t st);
+/// locate diagonals; returns number of rows without one
+int find_diagonals(Mat& A, cudaStream_t st);
+
+// pattern.cu
+struct IluPattern {
+	long long npos = 0;
+	DevBuf<int> posptr, lowerp, upperp;
+	bool built = false;
+};
+void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
+
+struct Levels {
+	int mode = B200_LEVELS_DAG;
+	int nlevels = 0;
+	std::vector<int> level_ptr;          ///< host copy of the level boundaries (nlevels+1)
+	DevBuf<int> d_level_ptr;
+	DevBuf<int> level_rows;              ///< DAG mode: rows ordered by level; contiguous: identity (unused)
+	bool built = false;
+};
+void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st);
+
+// factor.cu
+void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st);
+void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st);
+/// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
+/// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
+void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+                       int *d_changed, cudaStream_t st);
+void launch_invert_diag_blocks(const Mat& A, const double *src_vals, const int *positions_or_null,
+                               double *dst, bool dst_is_compact, cudaStream_t st);
+double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,
+                     double *d_scratch, cudaStream_t st);
+void diag_dominance(const Mat& A, const double *vals, double out[4], double *d_scratch,
+                    cudaStream_t st);
+
+// apply.cu
+enum TriKind { TRI_ILU_LOWER, TRI_ILU_UPPER, TRI_SGS_FWD, TRI_SGS_BWD, TRI_RELAX };
+struct TriArgs {
+	const double *vals = nullptr;    ///< factor (ILU) or matrix values (SGS/relax)
+	const double *dinv = nullptr;    ///< compact inverted diagonal blocks (SGS/relax), or nullptr
+	const double *rhs = nullptr;     ///< right-hand side vector of this sweep
+	const double *rscale = nullptr;  ///< optional scaling applied to rhs on the fly (or nullptr)
+	double *x = nullptr;             ///< vector updated by the sweep
+	const double *xsrc = nullptr;    ///< gather source; nullptr = x (in-place, chaotic)
+	const int *rows = nullptr;       ///< optional explicit row list (level scheduling)
+	int row_begin = 0, row_end = 0;  ///< range of rows (or of positions in `rows`)
+	bool descending = false;         ///< map CTAs to rows in descending order
+};
+void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t st);
+void launch_jacobi_apply(const Mat& A, const double *dinv, const double *r, double *z,
+                         cudaStream_t st);
+void launch_vec_scale_copy(long long n, const double *scale, const double *in, double *out,
+                           cudaStream_t st);   ///< out = scale ? scale*in : in
+void launch_vec_fill(long long n, double v, double *out, cudaStream_t st);
+
+// blas1.cu
+void launch_axpby(long long n, double p, double *z, double q, const double *x, cudaStream_t st);
+void launch_axpbypcz(long long n, double p, double *z, double q, const double *x, double r,
+                     const double *y, cudaStream_t st);
+/// out[0..nd) = dots of pairs (a[i], b[i]); result left on the device in d_out
+constexpr int MAX_DOTS = 8;
+constexpr int DOT_BLOCKS = 592;      // 148 SMs x 4
+/// d_out[i] = a[i] . b[i] for i < nd <= MAX_DOTS, deterministic two-stage reduction;
+/// d_partial must hold MAX_DOTS*DOT_BLOCKS doubles.  Result stays on the device.
+void launch_multi_dot(long long n, int nd, const double *const *a, const double *const *b,
+                      double *d_partial, double *d_out, cudaStream_t st);
+/// y += sum_l coef[l] * v[l]  for l < nv (coefficients read from device memory), nv <= 32 per call
+void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef,
+                       double *y, cudaStream_t st);
+
+// ---------------------------------------------------------------- preconditioner object
+
+/// Device counterpart of the SRPreconditioner subclasses (include/solverops_*.hpp of the reference)
+struct Prec {
+	b200_settings s;
+	Mat *A = nullptr;
+	cudaStream_t stream = 0;
+	bool threadedfactor = true, threadedapply = true;   ///< false: exact ("sequential") variant
+	bool is_ilu = false, is_jacobi_family = false, uses_levels = false;
+
+	IluPattern pl;
+	Levels levels;
+	DevBuf<double> ilu, scale, ytemp, dinv, xtemp, scratch, dot_partial;
+	DevBuf<int> flag;
+	DevBuf<double> hr, hz;              ///< staging for *_host entry points
+	bool computed = false;
+	int factor_sweeps_done = 0;         ///< sweeps used by the last compute (exact variants iterate)
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double compute_ms = 0, apply_ms = 0;
+
+	int dim() const { return A->nbrows*A->bs; }
+};
+
+void prec_compute(Prec& P, double precinfo[6]);
+void prec_apply(Prec& P, const double *d_r, double *d_z);
+void prec_apply_relax(Prec& P, const double *d_b, double *d_x, int maxits);
+
+// ---------------------------------------------------------------- Krylov drivers (krylov.cu)
+
+/// Operations a Krylov driver needs; the single-GPU implementation forwards to Mat/Prec, the
+/// multi-GPU one (dist.cu) adds the halo exchange and the all-reduce.
+struct KrylovOps {
+	long long n = 0;                                         ///< local vector length
+	cudaStream_t stream = 0;
+	virtual ~KrylovOps() {}
+	virtual void spmv(const double *x, double *y) = 0;
+	virtual void gemv3(double a, const double *x, double b, const double *y, double *z) = 0;
+	virtual void prec(const double *r, double *z) = 0;
+	/// out[i] = a[i].b[i], i < nd, summed over all ranks, returned on the host
+	virtual void dots(int nd, const double *const *a, const double *const *b, double *out) = 0;
+};
+
+void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, double *d_x,
+                  double tol, int maxiter, int restart, b200_solve_info *info);
+
+}  // namespace b200
+#endif

@@ -1,0 +1,537 @@
+/** \file factor.cu
+ * \brief Fine-grained asynchronous ILU(0) factorisation on the device (K1, K2, K3, K4, K10).
+ *
+ * Replaces, from the reference:
+ *   async_ilu0_factorize_kernel / executeILU0Factorization   src/kernels/kernels_ilu0_factorize.hpp:19-53,
+ *                                                            src/async_ilu_factor.cpp:154-177
+ *   async_block_ilu0_factorize / async_bilu0_sweeps          kernels_ilu0_factorize.hpp:71-98,
+ *                                                            src/async_blockilu_factor.cpp:187-204
+ *   initialisations                                          async_ilu_factor.cpp:47-58,110-151;
+ *                                                            async_blockilu_factor.cpp:63-94,207-254
+ *   diagonal block inversion                                 async_blockilu_factor.cpp:144-146,
+ *                                                            src/solverops_jacobi.cpp:43-45,141-147
+ *   nonlinear residual                                       async_ilu_factor.cpp:180-217,
+ *                                                            async_blockilu_factor.cpp:257-297
+ *   getScalingVector                                         src/rawsrmatrixutils.cpp:343-350
+ *   diagonal_dominance                                       src/matrix_properties.cpp:11-77
+ *
+ * Chaotic-iteration semantics kept from the reference: every entry is recomputed from A and the
+ * current iterate and written with ONE final store (never a partial sum,
+ * kernels_ilu0_factorize.hpp:34-40); reads of other entries are unordered relaxed loads that may
+ * observe old or new values.  One sweep = one pass over all stored entries; on the device a sweep
+ * is issued as a lower-triangle launch followed by an upper-triangle launch, so U entries see the
+ * L entries of the same sweep (the reference gets the same effect from processing a row's entries
+ * in order).
+ *
+ * Mapping.  Scalar: a group of LPR lanes per row, one entry per lane.  Block: a group of bs lanes
+ * per stored block ("entry-parallel", row index from browind), lane r owns row r of the block in
+ * registers; partner blocks are broadcast loads; right-division by U_jj is a register-resident
+ * bs x bs elimination with partial pivoting done redundantly per lane (no shuffles, no shared
+ * memory).  All of it is HBM/L2-bound: algorithmic bytes per sweep, scalar 32 nnz + 8 npos + 8 N,
+ * block nnzb (24 b^2 + 8) + 8 npos + 8 N.
+ */
+#include "common.cuh"
+#include <cub/device/device_reduce.cuh>
+
+namespace b200 {
+
+// Loads of the iterate that other CTAs may be rewriting: go to L2 (ld.global.cg) so that values
+// written earlier in the same launch are observed (L1 is not coherent across SMs).
+__device__ __forceinline__ double ld_iter(const double *p) { return __ldcg(p); }
+
+// ------------------------------------------------------------------ dense helpers (registers)
+
+/// Solves x * D = s for the row vector x, D given column-major in registers (D(i,j) = d[j*BS+i]).
+/// Equivalent to M x^T = s^T with M = D^T, i.e. M(i,j) = d[i*BS+j]: Gaussian elimination with
+/// partial pivoting, fully unrolled.  Stands in for `sum * U_jj.inverse()`
+/// (kernels_ilu0_factorize.hpp:91) and for `.inverse()` itself (row r of D^-1 solves x D = e_r).
+template <int BS>
+__device__ __forceinline__ void solve_right(double (&d)[BS*BS], double (&s)[BS], double (&x)[BS])
+{
+	double pinv[BS];
+#pragma unroll
+	for(int p = 0; p < BS; p++) {
+		// bring the largest |M(q,p)|, q >= p, to row p by successive conditional swaps
+#pragma unroll
+		for(int q = p+1; q < BS; q++) {
+			const bool sw = fabs(d[q*BS+p]) > fabs(d[p*BS+p]);
+#pragma unroll
+			for(int j = p; j < BS; j++) {
+				const double a = d[p*BS+j], b = d[q*BS+j];
+				d[p*BS+j] = sw ? b : a;
+				d[q*BS+j] = sw ? a : b;
+			}
+			const double a = s[p], b = s[q];
+			s[p] = sw ? b : a;
+			s[q] = sw ? a : b;
+		}
+		pinv[p] = 1.0/d[p*BS+p];
+#pragma unroll
+		for(int i = p+1; i < BS; i++) {
+			const double f = d[i*BS+p]*pinv[p];
+#pragma unroll
+			for(int j = p+1; j < BS; j++)
+				d[i*BS+j] = fma(-f, d[p*BS+j], d[i*BS+j]);
+			s[i] = fma(-f, s[p], s[i]);
+		}
+	}
+#pragma unroll
+	for(int i = BS-1; i >= 0; i--) {
+		double t = s[i];
+#pragma unroll
+		for(int j = i+1; j < BS; j++)
+			t = fma(-d[i*BS+j], x[j], t);
+		x[i] = t*pinv[i];
+	}
+}
+
+/// Loads a whole column-major block into registers
+template <int BS, bool ITER>
+__device__ __forceinline__ void load_block(const double *p, double (&d)[BS*BS])
+{
+	if(BS % 2 == 0) {
+		const double2 *p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+		for(int e = 0; e < BS*BS/2; e++) {
+			const double2 v = ITER ? __ldcg(p2 + e) : __ldg(p2 + e);
+			d[2*e] = v.x; d[2*e+1] = v.y;
+		}
+	} else {
+#pragma unroll
+		for(int e = 0; e < BS*BS; e++) d[e] = ITER ? __ldcg(p + e) : __ldg(p + e);
+	}
+}
+
+// ------------------------------------------------------------------ scaling vector
+
+template <int BS>
+__global__ void scaling_vector_kernel(const int nbrows, const double *__restrict__ vals,
+                                      const int *__restrict__ diagind, double *__restrict__ scale)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= (long long)nbrows*BS) return;
+	const int row = (int)(i / BS), j = (int)(i % BS);
+	scale[i] = 1.0/sqrt(vals[(size_t)diagind[row]*BS*BS + j*BS + j]);
+}
+
+void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st)
+{
+	const long long n = (long long)A.nbrows*A.bs;
+	if(n == 0) return;
+	const int grid = div_up(n, 256);
+	switch(A.bs) {
+	case 1: scaling_vector_kernel<1><<<grid,256,0,st>>>(A.nbrows, A.vals, A.diagind, scale); break;
+	case 4: scaling_vector_kernel<4><<<grid,256,0,st>>>(A.nbrows, A.vals, A.diagind, scale); break;
+	case 5: scaling_vector_kernel<5><<<grid,256,0,st>>>(A.nbrows, A.vals, A.diagind, scale); break;
+	default: throw Error("scaling: unsupported block size");
+	}
+	B200_LAUNCHED();
+}
+
+// ------------------------------------------------------------------ scalar ILU(0)
+
+enum { PH_ALL = 0, PH_LOWER = 1, PH_UPPER = 2 };
+enum { MODE_SWEEP = 0, MODE_RESIDUAL = 1, MODE_INIT_SGS = 2, MODE_INIT_ORIG = 3 };
+
+/// One (partial) asynchronous sweep, or the residual, or an initialisation, of scalar ILU(0).
+template <int LPR, bool SCALE, int PHASE, int MODE>
+__global__ void __launch_bounds__(256)
+scalar_ilu0_kernel(const int nrows, const int *__restrict__ rowptr, const int *__restrict__ colind,
+                   const int *__restrict__ diagind, const double *__restrict__ avals,
+                   const int *__restrict__ posptr, const int *__restrict__ lowerp,
+                   const int *__restrict__ upperp, const double *__restrict__ scale,
+                   double *ilu, double *__restrict__ resout, int *__restrict__ changed)
+{
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	const int row = (int)(tid / LPR);
+	const int lane = (int)(tid % LPR);
+	double res = 0;
+	if(row < nrows) {
+		const int s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+		const double srow = SCALE ? __ldg(scale + row) : 1.0;
+		for(int j = s + lane; j < e; j += LPR) {
+			const int col = __ldg(colind + j);
+			const bool lower = row > col;
+			if(PHASE == PH_LOWER && !lower) continue;
+			if(PHASE == PH_UPPER && lower) continue;
+			double sum = __ldg(avals + j);
+			if(SCALE) { sum *= srow; sum *= __ldg(scale + col); }
+
+			if(MODE == MODE_INIT_ORIG) { ilu[j] = sum; continue; }
+			if(MODE == MODE_INIT_SGS) {
+				// L' = L D^-1 on the (scaled) matrix: async_ilu_factor.cpp:110-133; the scaled
+				// diagonal is a_cc*s_c*s_c (the reference indexes `scale` out of bounds there)
+				if(lower) {
+					const double sc = SCALE ? __ldg(scale + col) : 1.0;
+					const double dg = __ldg(avals + __ldg(diagind + col));
+					sum *= SCALE ? 1.0/(dg*sc*sc) : 1.0/dg;
+				}
+				ilu[j] = sum;
+				continue;
+			}
+
+			const int ps = __ldg(posptr + j), pe = __ldg(posptr + j + 1);
+			for(int k = ps; k < pe; k++)
+				sum = fma(-ld_iter(ilu + __ldg(lowerp + k)), ld_iter(ilu + __ldg(upperp + k)), sum);
+
+			if(MODE == MODE_RESIDUAL) {
+				if(lower) sum -= ld_iter(ilu + j) * ld_iter(ilu + __ldg(diagind + col));
+				else sum -= ld_iter(ilu + j);
+				res += fabs(sum);
+			} else {
+				if(lower) sum = sum / ld_iter(ilu + __ldg(diagind + col));
+				if(changed && ld_iter(ilu + j) != sum) *changed = 1;
+				ilu[j] = sum;                                   // single final store
+			}
+		}
+	}
+	if(MODE == MODE_RESIDUAL) {
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
+		__shared__ double wsum[8];
+		const int w = threadIdx.x >> 5;
+		if((threadIdx.x & 31) == 0) wsum[w] = res;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			double t = 0;
+			for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
+			atomicAdd(resout, t);
+		}
+	}
+}
+
+template <int PHASE, int MODE>
+static void launch_scalar(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
+                          double *resout, int *changed, cudaStream_t st)
+{
+	const int n = A.nbrows;
+	const double avg = A.avg_row_len;
+	const int *pp = pl ? pl->posptr.p : nullptr, *lp = pl ? pl->lowerp.p : nullptr,
+		*up = pl ? pl->upperp.p : nullptr;
+#define B200_SC_CASE(L)                                                                             \
+	{                                                                                               \
+		const int grid = div_up((long long)n*L, 256);                                               \
+		if(scale) scalar_ilu0_kernel<L,true,PHASE,MODE><<<grid,256,0,st>>>(n, A.browptr, A.bcolind,   \
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);                            \
+		else scalar_ilu0_kernel<L,false,PHASE,MODE><<<grid,256,0,st>>>(n, A.browptr, A.bcolind,       \
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);                            \
+	}
+	if(avg <= 5) B200_SC_CASE(4)
+	else if(avg <= 12) B200_SC_CASE(8)
+	else if(avg <= 24) B200_SC_CASE(16)
+	else B200_SC_CASE(32)
+#undef B200_SC_CASE
+	B200_LAUNCHED();
+}
+
+// ------------------------------------------------------------------ block ILU(0)
+
+/// One (partial) asynchronous sweep / residual / initialisation of point-block ILU(0).
+/// A group of BS lanes per stored block; lane r holds row r of the block.
+template <int BS, bool SCALE, int PHASE, int MODE>
+__global__ void __launch_bounds__(256)
+block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
+                  const int *__restrict__ browind, const int *__restrict__ diagind,
+                  const double *__restrict__ avals, const int *__restrict__ posptr,
+                  const int *__restrict__ lowerp, const int *__restrict__ upperp,
+                  const double *__restrict__ scale, double *ilu, double *__restrict__ resout,
+                  int *__restrict__ changed)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long entry = warp*GPW + g;
+	double res = 0;
+	bool active = (g < GPW) && (entry < nnzb);
+	int row = 0, col = 0;
+	bool lower = false;
+	if(active) {
+		row = __ldg(browind + entry);
+		col = __ldg(bcolind + entry);
+		lower = row > col;
+		if(PHASE == PH_LOWER && !lower) active = false;
+		if(PHASE == PH_UPPER && lower) active = false;
+	}
+	if(active) {
+		double sum[BS];
+		const double *ap = avals + (size_t)entry*BS2 + r;
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] = __ldg(ap + c*BS);
+		if(SCALE) {
+			// scaleBlock: val(i,j) *= scale[brow*bs+i]*scale[bcol*bs+j]  (kernels_ilu0_factorize.hpp:61-69)
+			const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+		}
+
+		if(MODE == MODE_SWEEP || MODE == MODE_RESIDUAL) {
+			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
+			for(int k = ps; k < pe; k++) {
+				const double *lb = ilu + (size_t)__ldg(lowerp + k)*BS2 + r;
+				const double *ub = ilu + (size_t)__ldg(upperp + k)*BS2;
+				double lr[BS], u[BS2];
+#pragma unroll
+				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
+				load_block<BS,true>(ub, u);
+#pragma unroll
+				for(int c = 0; c < BS; c++)
+#pragma unroll
+					for(int m = 0; m < BS; m++)
+						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
+			}
+		}
+
+		double *op = ilu + (size_t)entry*BS2 + r;
+		if(MODE == MODE_RESIDUAL) {
+			double cur[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++) cur[c] = ld_iter(op + c*BS);
+			if(lower) {
+				double d[BS2];
+				load_block<BS,true>(ilu + (size_t)__ldg(diagind + col)*BS2, d);
+#pragma unroll
+				for(int c = 0; c < BS; c++)
+#pragma unroll
+					for(int m = 0; m < BS; m++)
+						sum[c] = fma(-cur[m], d[c*BS+m], sum[c]);
+			} else {
+#pragma unroll
+				for(int c = 0; c < BS; c++) sum[c] -= cur[c];
+			}
+#pragma unroll
+			for(int c = 0; c < BS; c++) res += fabs(sum[c]);
+		}
+		else {
+			if(lower && MODE != MODE_INIT_ORIG) {
+				double d[BS2], x[BS];
+				const size_t dpos = (size_t)__ldg(diagind + col)*BS2;
+				if(MODE == MODE_INIT_SGS) {
+					// D = (scaled) diagonal block of A: async_blockilu_factor.cpp:221-250
+					load_block<BS,false>(avals + dpos, d);
+					if(SCALE) {
+#pragma unroll
+						for(int c = 0; c < BS; c++)
+#pragma unroll
+							for(int m = 0; m < BS; m++)
+								d[c*BS+m] *= __ldg(scale + (size_t)col*BS + m)*__ldg(scale + (size_t)col*BS + c);
+					}
+				} else
+					load_block<BS,true>(ilu + dpos, d);
+				solve_right<BS>(d, sum, x);
+				if(changed) {
+					bool ch = false;
+#pragma unroll
+					for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != x[c]);
+					if(ch) *changed = 1;
+				}
+#pragma unroll
+				for(int c = 0; c < BS; c++) op[c*BS] = x[c];
+			} else {
+				if(changed) {
+					bool ch = false;
+#pragma unroll
+					for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != sum[c]);
+					if(ch) *changed = 1;
+				}
+#pragma unroll
+				for(int c = 0; c < BS; c++) op[c*BS] = sum[c];
+			}
+		}
+	}
+	if(MODE == MODE_RESIDUAL) {
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
+		__shared__ double wsum[8];
+		const int w = threadIdx.x >> 5;
+		if(lane == 0) wsum[w] = res;
+		__syncthreads();
+		if(threadIdx.x == 0) {
+			double t = 0;
+			for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
+			atomicAdd(resout, t);
+		}
+	}
+}
+
+template <int BS, int PHASE, int MODE>
+static void launch_block(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
+                         double *resout, int *changed, cudaStream_t st)
+{
+	constexpr int GPW = 32/BS;
+	const long long nwarps = (A.nnzb + GPW - 1)/GPW;
+	const int grid = div_up(nwarps*32, 256);
+	const int *pp = pl ? pl->posptr.p : nullptr, *lp = pl ? pl->lowerp.p : nullptr,
+		*up = pl ? pl->upperp.p : nullptr;
+	if(scale)
+		block_ilu0_kernel<BS,true,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);
+	else
+		block_ilu0_kernel<BS,false,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);
+	B200_LAUNCHED();
+}
+
+template <int PHASE, int MODE>
+static void launch_any(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
+                       double *resout, int *changed, cudaStream_t st)
+{
+	if(A.nnzb == 0) return;
+	switch(A.bs) {
+	case 1: launch_scalar<PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
+	case 4: launch_block<4,PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
+	case 5: launch_block<5,PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
+	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+	}
+}
+
+void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st)
+{
+	if(fact_init == B200_INIT_F_NONE) return;
+	if(A.bs > 1 && fact_init == B200_INIT_F_ZERO) {
+		// the block version really zeroes (async_blockilu_factor.cpp:65-69); the scalar one falls
+		// through into INIT_F_ORIGINAL (async_ilu_factor.cpp:48-54) - both replicated
+		B200_CUDA(cudaMemsetAsync(ilu, 0, (size_t)A.nnzb*A.bs*A.bs*sizeof(double), st));
+		return;
+	}
+	if(fact_init == B200_INIT_F_SGS)
+		launch_any<PH_ALL,MODE_INIT_SGS>(A, nullptr, scale, ilu, nullptr, nullptr, st);
+	else
+		launch_any<PH_ALL,MODE_INIT_ORIG>(A, nullptr, scale, ilu, nullptr, nullptr, st);
+}
+
+void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+                       int *d_changed, cudaStream_t st)
+{
+	launch_any<PH_LOWER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st);
+	launch_any<PH_UPPER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st);
+}
+
+double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,
+                     double *d_scratch, cudaStream_t st)
+{
+	B200_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(double), st));
+	launch_any<PH_ALL,MODE_RESIDUAL>(A, &pl, scale, const_cast<double*>(ilu), d_scratch, nullptr, st);
+	double r = 0;
+	B200_CUDA(cudaMemcpyAsync(&r, d_scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	return r;
+}
+
+// ------------------------------------------------------------------ diagonal block inversion
+
+/// dst block i <- inverse of src block at positions[i] (or i).  Works in place.
+template <int BS>
+__global__ void __launch_bounds__(256)
+invert_blocks_kernel(const int nbrows, const double *src, const int *__restrict__ positions,
+                     double *dst, const bool dst_compact)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long rowl = warp*GPW + g;
+	const bool active = (g < GPW) && (rowl < nbrows);
+	double d[BS2], e[BS], x[BS];
+	size_t spos = 0;
+	if(active) {
+		spos = positions ? (size_t)__ldg(positions + rowl) : (size_t)rowl;
+		load_block<BS,true>(src + spos*BS2, d);
+#pragma unroll
+		for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
+		solve_right<BS>(d, e, x);          // row r of the inverse
+	}
+	__syncwarp();                          // all lanes have read the block before anyone overwrites it
+	if(active) {
+		double *op = dst + (dst_compact ? (size_t)rowl : spos)*BS2 + r;
+#pragma unroll
+		for(int c = 0; c < BS; c++) op[c*BS] = x[c];
+	}
+}
+
+__global__ void invert_scalars_kernel(const int n, const double *__restrict__ src,
+                                      const int *__restrict__ positions, double *__restrict__ dst)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) dst[i] = 1.0/src[positions ? positions[i] : i];
+}
+
+void launch_invert_diag_blocks(const Mat& A, const double *src_vals, const int *positions,
+                               double *dst, bool dst_is_compact, cudaStream_t st)
+{
+	if(A.nbrows == 0) return;
+	if(A.bs == 1) {
+		// only used for the Jacobi-type objects (scalar_jacobi_setup, solverops_jacobi.cpp:141-147)
+		invert_scalars_kernel<<<div_up(A.nbrows,256),256,0,st>>>(A.nbrows, src_vals, positions, dst);
+		B200_LAUNCHED();
+		return;
+	}
+	const int GPW = 32/A.bs;
+	const long long nwarps = ((long long)A.nbrows + GPW - 1)/GPW;
+	const int grid = div_up(nwarps*32, 256);
+	switch(A.bs) {
+	case 4: invert_blocks_kernel<4><<<grid,256,0,st>>>(A.nbrows, src_vals, positions, dst, dst_is_compact); break;
+	case 5: invert_blocks_kernel<5><<<grid,256,0,st>>>(A.nbrows, src_vals, positions, dst, dst_is_compact); break;
+	default: throw Error("block inverse: unsupported block size");
+	}
+	B200_LAUNCHED();
+}
+
+// ------------------------------------------------------------------ diagonal dominance
+
+template <int BS>
+__global__ void diag_dom_kernel(const int nbrows, const int *__restrict__ browptr,
+                                const int *__restrict__ diagind, const double *__restrict__ vals,
+                                double *__restrict__ ddl, double *__restrict__ ddu)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= (long long)nbrows*BS) return;
+	const int row = (int)(i / BS), r = (int)(i % BS);
+	constexpr int BS2 = BS*BS;
+	const int dp = diagind[row];
+	double l = 0, u = 0;
+	for(int c = 0; c < BS; c++)
+		if(c != r) u += fabs(vals[(size_t)dp*BS2 + c*BS + r]);
+	for(int jj = dp+1; jj < browptr[row+1]; jj++)
+		for(int c = 0; c < BS; c++) u += fabs(vals[(size_t)jj*BS2 + c*BS + r]);
+	for(int jj = browptr[row]; jj < dp; jj++)
+		for(int c = 0; c < BS; c++) l += fabs(vals[(size_t)jj*BS2 + c*BS + r]);
+	ddl[i] = 1.0 - l;
+	ddu[i] = 1.0 - u/fabs(vals[(size_t)dp*BS2 + r*BS + r]);
+}
+
+void diag_dominance(const Mat& A, const double *vals, double out[4], double * /*d_scratch*/,
+                    cudaStream_t st)
+{
+	const long long n = (long long)A.nbrows*A.bs;
+	DevBuf<double> ddl, ddu, red;
+	ddl.alloc(n); ddu.alloc(n); red.alloc(4);
+	const int grid = div_up(n, 256);
+	switch(A.bs) {
+	case 1: diag_dom_kernel<1><<<grid,256,0,st>>>(A.nbrows, A.browptr, A.diagind, vals, ddl, ddu); break;
+	case 4: diag_dom_kernel<4><<<grid,256,0,st>>>(A.nbrows, A.browptr, A.diagind, vals, ddl, ddu); break;
+	case 5: diag_dom_kernel<5><<<grid,256,0,st>>>(A.nbrows, A.browptr, A.diagind, vals, ddl, ddu); break;
+	default: throw Error("diag dominance: unsupported block size");
+	}
+	B200_LAUNCHED();
+	size_t tb = 0, t2 = 0;
+	cub::DeviceReduce::Sum(nullptr, tb, ddl.p, red.p, (int)n, st);
+	cub::DeviceReduce::Min(nullptr, t2, ddl.p, red.p, (int)n, st);
+	DevBuf<char> tmp;
+	tmp.alloc(std::max(tb, t2));
+	size_t t = tmp.n;
+	B200_CUDA(cub::DeviceReduce::Sum(tmp.p, t, ddl.p, red.p + 0, (int)n, st)); t = tmp.n;
+	B200_CUDA(cub::DeviceReduce::Min(tmp.p, t, ddl.p, red.p + 1, (int)n, st)); t = tmp.n;
+	B200_CUDA(cub::DeviceReduce::Sum(tmp.p, t, ddu.p, red.p + 2, (int)n, st)); t = tmp.n;
+	B200_CUDA(cub::DeviceReduce::Min(tmp.p, t, ddu.p, red.p + 3, (int)n, st));
+	g_launches.fetch_add(4);
+	double h[4];
+	B200_CUDA(cudaMemcpyAsync(h, red.p, 4*sizeof(double), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	// {lower avg, lower min, upper avg, upper min}  (matrix_properties.cpp:76)
+	out[0] = h[0]/(double)n; out[1] = h[1]; out[2] = h[2]/(double)n; out[3] = h[3];
+}
+
+}  // namespace b200

@@ -1,0 +1,308 @@
+/** \file pattern.cu
+ * \brief Setup built on the device (K12): ILU(0) position lists and level schedules.
+ *
+ * ILU positions replace compute_ILU_positions_CSR_CSR (src/ilu_pattern.cpp:32-163 of the reference:
+ * serial, linear inner_search).  Here: one thread per stored entry counts its (L-position,
+ * U-position) pairs using binary search in the sorted upper part of the partner row, an exclusive
+ * scan (CUB) gives posptr, and a second pass fills lowerp/upperp in the same ascending-k order, so
+ * the three arrays are bit-identical to the reference's.
+ *
+ * Levels: (a) CONTIGUOUS reproduces computeLevels (src/levelschedule.cpp:12-71) exactly.  With
+ * sorted columns and a structurally symmetric pattern its std::list bookkeeping reduces to: the
+ * level starting at row s extends over consecutive rows r whose largest lower column d(r) < s.
+ * (b) DAG computes true dependency wavefronts level[i] = 1 + max_{j<i, a_ij != 0} level[j] by
+ * chaotic relaxation to the (unique) fixed point, then orders rows by level with a stable radix
+ * sort (CUB).
+ */
+#include "common.cuh"
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_radix_sort.cuh>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ ILU positions
+
+__device__ __forceinline__ int search_sorted(const int *__restrict__ a, int lo, int hi, const int key)
+{
+	// [lo, hi) sorted ascending; returns position of key or -1
+	hi -= 1;
+	while(lo <= hi) {
+		const int mid = (lo + hi) >> 1;
+		const int c = __ldg(a + mid);
+		if(c == key) return mid;
+		if(c < key) lo = mid + 1; else hi = mid - 1;
+	}
+	return -1;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+ilu_positions_kernel(const long long nnzb, const int *__restrict__ browptr,
+                     const int *__restrict__ bcolind, const int *__restrict__ diagind,
+                     const int *__restrict__ browind, const int *__restrict__ posptr,
+                     int *__restrict__ counts, int *__restrict__ lowerp, int *__restrict__ upperp)
+{
+	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(j >= nnzb) return;
+	const int row = __ldg(browind + j);
+	const int col = __ldg(bcolind + j);
+	// l_ij (row > col): k-columns below col;  u_ij: k-columns below row   (ilu_pattern.cpp:46-48, :62-63)
+	const int lim = row > col ? col : row;
+	const int rs = __ldg(browptr + row), re = __ldg(browptr + row + 1);
+	int cnt = 0;
+	const int base = FILL ? __ldg(posptr + j) : 0;
+	for(int k = rs; k < re; k++) {
+		const int kc = __ldg(bcolind + k);
+		if(kc >= lim) break;
+		const int ipos = search_sorted(bcolind, __ldg(diagind + kc), __ldg(browptr + kc + 1), col);
+		if(ipos >= 0) {
+			if(FILL) { lowerp[base + cnt] = k; upperp[base + cnt] = ipos; }
+			cnt++;
+		}
+	}
+	if(!FILL) counts[j] = cnt;
+}
+
+/// 64-bit total of the per-entry counts (the reference accumulates in int, ilu_pattern.cpp:87)
+__global__ void __launch_bounds__(256)
+sum_counts_kernel(const long long n, const int *__restrict__ counts, unsigned long long *__restrict__ total)
+{
+	unsigned long long s = 0;
+	for(long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n;
+	    i += (long long)gridDim.x*blockDim.x)
+		s += (unsigned long long)counts[i];
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+	if((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
+void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
+{
+	const long long nnzb = A.nnzb;
+	pl.posptr.alloc(nnzb + 1);
+	pl.npos = 0;
+	if(nnzb == 0) {
+		B200_CUDA(cudaMemsetAsync(pl.posptr, 0, sizeof(int), st));
+		pl.built = true;
+		return;
+	}
+	DevBuf<int> counts;
+	counts.alloc(nnzb + 1);
+	B200_CUDA(cudaMemsetAsync(counts.p + nnzb, 0, sizeof(int), st));
+	const int grid = div_up(nnzb, 256);
+	ilu_positions_kernel<false><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
+	                                                  nullptr, counts, nullptr, nullptr);
+	B200_LAUNCHED();
+
+	// total in 64 bits first
+	DevBuf<unsigned long long> d_total;
+	d_total.alloc(1);
+	B200_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+	sum_counts_kernel<<<std::min(grid, 148*8), 256, 0, st>>>(nnzb, counts, d_total);
+	B200_LAUNCHED();
+	unsigned long long utotal = 0;
+	B200_CUDA(cudaMemcpyAsync(&utotal, d_total.p, sizeof(utotal), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	const long long total = (long long)utotal;
+	if(total >= 2147483647LL)
+		throw Error("ILU position list exceeds int32 indexing (npos = " + std::to_string(total) + ")");
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, pl.posptr.p, (int)(nnzb + 1), st);
+	DevBuf<char> tmp;
+	tmp.alloc(tb);
+	B200_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, pl.posptr.p, (int)(nnzb + 1), st));
+	g_launches.fetch_add(1);
+
+	pl.npos = total;
+	pl.lowerp.alloc(std::max<long long>(total, 1));
+	pl.upperp.alloc(std::max<long long>(total, 1));
+	if(total > 0) {
+		ilu_positions_kernel<true><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind,
+		                                                 A.browind, pl.posptr, nullptr, pl.lowerp,
+		                                                 pl.upperp);
+		B200_LAUNCHED();
+	}
+	B200_CUDA(cudaStreamSynchronize(st));
+	pl.built = true;
+}
+
+// ------------------------------------------------------------------ structural symmetry check
+
+__global__ void symmetry_check_kernel(const long long nnzb, const int *__restrict__ browptr,
+                                      const int *__restrict__ bcolind,
+                                      const int *__restrict__ browind, int *__restrict__ nbad)
+{
+	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(j >= nnzb) return;
+	const int row = __ldg(browind + j), col = __ldg(bcolind + j);
+	if(search_sorted(bcolind, __ldg(browptr + col), __ldg(browptr + col + 1), row) < 0)
+		atomicAdd(nbad, 1);
+}
+
+// ------------------------------------------------------------------ contiguous levels
+
+/// One CTA walks the rows in order.  d(r) = largest column below r in row r (-1 if none) is staged
+/// in shared memory by all threads; warp 0 then finds the level boundaries with ballots.
+__global__ void __launch_bounds__(1024)
+contiguous_levels_kernel(const int nbrows, const int *__restrict__ browptr,
+                         const int *__restrict__ bcolind, const int *__restrict__ diagind,
+                         int *__restrict__ levels, int *__restrict__ nlevels_out)
+{
+	constexpr int CHUNK = 8192;
+	__shared__ int d[CHUNK];
+	__shared__ int s_level_start, s_count;
+	if(threadIdx.x == 0) { s_level_start = 0; s_count = 1; levels[0] = 0; }
+	__syncthreads();
+
+	for(int base = 0; base < nbrows; base += CHUNK) {
+		const int len = min(CHUNK, nbrows - base);
+		for(int t = threadIdx.x; t < len; t += blockDim.x) {
+			const int r = base + t;
+			const int dp = diagind[r];
+			d[t] = (dp > browptr[r]) ? bcolind[dp-1] : -1;
+		}
+		__syncthreads();
+		if(threadIdx.x < 32) {
+			const int lane = threadIdx.x;
+			int s = s_level_start, cnt = s_count;
+			int t = 0;
+			while(t < len) {
+				const int tt = t + lane;
+				const bool brk = (tt < len) && (d[tt] >= s) && (base + tt > s);
+				const unsigned m = __ballot_sync(0xffffffffu, brk);
+				if(m == 0) { t += 32; continue; }
+				const int f = __ffs(m) - 1;
+				s = base + t + f;                  // row s starts a new level
+				if(lane == 0) levels[cnt] = s;
+				cnt++;
+				t = t + f + 1;
+			}
+			if(lane == 0) { s_level_start = s; s_count = cnt; }
+		}
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) {
+		levels[s_count] = nbrows;
+		*nlevels_out = s_count;            // number of levels; entries written = s_count+1
+	}
+}
+
+// ------------------------------------------------------------------ DAG levels
+
+__global__ void __launch_bounds__(256)
+dag_relax_kernel(const int nbrows, const int *__restrict__ browptr, const int *__restrict__ bcolind,
+                 const int *__restrict__ diagind, int *level, int *__restrict__ changed)
+{
+	const int row = blockIdx.x*blockDim.x + threadIdx.x;
+	if(row >= nbrows) return;
+	int lv = 0;
+	const int s = __ldg(browptr + row), e = __ldg(diagind + row);
+	for(int jj = s; jj < e; jj++) {
+		const int l = __ldcg(level + __ldg(bcolind + jj)) + 1;
+		lv = max(lv, l);
+	}
+	if(lv != __ldcg(level + row)) {
+		level[row] = lv;
+		*changed = 1;
+	}
+}
+
+__global__ void iota_kernel(int n, int *out)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) out[i] = i;
+}
+
+__global__ void level_bounds_kernel(int n, const int *__restrict__ sorted_level, int *__restrict__ level_ptr)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const int l = sorted_level[i];
+	if(i == 0 || sorted_level[i-1] != l) level_ptr[l] = i;
+	if(i == n-1) level_ptr[l+1] = n;
+}
+
+void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st)
+{
+	const int n = A.nbrows;
+	lv.mode = mode;
+	lv.nlevels = 0;
+	lv.level_ptr.assign(1, 0);
+	if(n == 0) { lv.built = true; return; }
+
+	if(mode == B200_LEVELS_CONTIGUOUS) {
+		// "(jnode must be found because the sparsity structure is symmetric)" levelschedule.cpp:55-57
+		DevBuf<int> d_bad;
+		d_bad.alloc(1);
+		B200_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+		symmetry_check_kernel<<<div_up(A.nnzb, 256), 256, 0, st>>>(A.nnzb, A.browptr, A.bcolind,
+		                                                          A.browind, d_bad);
+		B200_LAUNCHED();
+		int bad = 0;
+		B200_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		if(bad) throw Error("Faulty dependency list!");
+
+		lv.d_level_ptr.alloc((size_t)n + 1);
+		DevBuf<int> d_nl;
+		d_nl.alloc(1);
+		contiguous_levels_kernel<<<1, 1024, 0, st>>>(n, A.browptr, A.bcolind, A.diagind,
+		                                             lv.d_level_ptr, d_nl);
+		B200_LAUNCHED();
+		B200_CUDA(cudaMemcpyAsync(&lv.nlevels, d_nl, sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		lv.level_ptr.resize(lv.nlevels + 1);
+		B200_CUDA(cudaMemcpyAsync(lv.level_ptr.data(), lv.d_level_ptr, (lv.nlevels+1)*sizeof(int),
+		                          cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		lv.level_rows.release();
+		lv.built = true;
+		return;
+	}
+
+	// DAG wavefronts
+	DevBuf<int> level, changed, rows_in, level_sorted;
+	level.alloc(n);
+	changed.alloc(1);
+	B200_CUDA(cudaMemsetAsync(level, 0, n*sizeof(int), st));
+	const int grid = div_up(n, 256);
+	int h_changed = 1, rounds = 0;
+	while(h_changed) {
+		B200_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+		for(int rep = 0; rep < 8; rep++) {
+			dag_relax_kernel<<<grid, 256, 0, st>>>(n, A.browptr, A.bcolind, A.diagind, level, changed);
+			B200_LAUNCHED();
+		}
+		B200_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		if(++rounds > n + 8) throw Error("DAG level relaxation did not converge");
+	}
+	rows_in.alloc(n);
+	level_sorted.alloc(n);
+	lv.level_rows.alloc(n);
+	iota_kernel<<<grid, 256, 0, st>>>(n, rows_in);
+	B200_LAUNCHED();
+	size_t tb = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tb, level.p, level_sorted.p, rows_in.p, lv.level_rows.p,
+	                                n, 0, 32, st);
+	DevBuf<char> tmp;
+	tmp.alloc(tb);
+	B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, level.p, level_sorted.p, rows_in.p,
+	                                          lv.level_rows.p, n, 0, 32, st));
+	g_launches.fetch_add(1);
+	int maxlevel = 0;
+	B200_CUDA(cudaMemcpyAsync(&maxlevel, level_sorted.p + (n-1), sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	lv.nlevels = maxlevel + 1;
+	lv.d_level_ptr.alloc((size_t)lv.nlevels + 1);
+	level_bounds_kernel<<<grid, 256, 0, st>>>(n, level_sorted, lv.d_level_ptr);
+	B200_LAUNCHED();
+	lv.level_ptr.resize(lv.nlevels + 1);
+	B200_CUDA(cudaMemcpyAsync(lv.level_ptr.data(), lv.d_level_ptr, (lv.nlevels+1)*sizeof(int),
+	                          cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	lv.built = true;
+}
+
+}  // namespace b200

@@ -1,0 +1,289 @@
+/** \file precond.cu
+ * \brief compute() / apply() / apply_relax() of the device preconditioner objects.
+ *
+ * Host-side sweep drivers (the L2 layer of SURVEY.md section 1), one per reference class:
+ *   AsyncILU0_SRPreconditioner / AsyncBlockILU0_SRPreconditioner   src/solverops_ilu0.cpp:56-383
+ *   scalar_ilu0_factorize / block_ilu0_factorize                   src/async_ilu_factor.cpp:37-97,
+ *                                                                  src/async_blockilu_factor.cpp:47-149
+ *   AsyncSGS_SRPreconditioner / AsyncBlockSGS_SRPreconditioner     src/solverops_sgs.cpp:32-203
+ *   JacobiSRPreconditioner / BJacobiSRPreconditioner               src/solverops_jacobi.cpp:31-220
+ *   ChaoticRelaxation / ChaoticBlockRelaxation                     src/relaxation_chaotic.cpp:22-123
+ *   Level_SGS / Level_BSGS                                         src/solverops_levels_sgs.cpp:54-221
+ *   Async_Level_ILU0 / Async_Level_BlockILU0                       src/solverops_levels_ilu0.cpp:58-192
+ *   NoPreconditioner                                               src/solverops_base.cpp:27-43
+ *
+ * "Sequential" variants (BLASTED_SEQILU0 / SFILU0 / SAPILU0: threadedfactor/threadedapply false,
+ * src/solverfactory.cpp:93-107,163-180) are the EXACT operations on the device: the factorisation
+ * iterates asynchronous sweeps until no entry changes bitwise (the ILU(0) fixed point, which one
+ * sequential pass of the same row kernel produces in the reference), and the triangular solves run
+ * level-scheduled substitution.
+ */
+#include "common.cuh"
+
+namespace b200 {
+
+static void ensure_events(Prec& P)
+{
+	if(!P.ev0) {
+		B200_CUDA(cudaEventCreate(&P.ev0));
+		B200_CUDA(cudaEventCreate(&P.ev1));
+	}
+}
+
+static double elapsed(Prec& P)
+{
+	B200_CUDA(cudaEventSynchronize(P.ev1));
+	float ms = 0;
+	B200_CUDA(cudaEventElapsedTime(&ms, P.ev0, P.ev1));
+	return ms;
+}
+
+// ------------------------------------------------------------------ compute
+
+void prec_compute(Prec& P, double precinfo[6])
+{
+	Mat& A = *P.A;
+	cudaStream_t st = P.stream;
+	const int type = P.s.prectype;
+	ensure_events(P);
+	if(precinfo) for(int i = 0; i < 6; i++) precinfo[i] = 0;     // PrecInfo() value-initialised
+
+	if(type == B200_NO_PREC) { P.computed = true; return; }
+	if(!A.has_diag) throw Error("preconditioner needs a structurally non-zero diagonal");
+	if(!P.scratch.p) P.scratch.alloc(8);
+
+	const bool first = !P.computed;
+	B200_CUDA(cudaEventRecord(P.ev0, st));
+
+	if(P.is_jacobi_family) {
+		// BJacobiSRPreconditioner::compute, solverops_jacobi.cpp:31-48 / scalar_jacobi_setup :141-147
+		if(!P.dinv.p) P.dinv.alloc((size_t)A.nbrows*A.bs*A.bs);
+		launch_invert_diag_blocks(A, A.vals, A.diagind, P.dinv, true, st);
+		if(first) {
+			// ytemp allocated and zeroed once: solverops_sgs.cpp:36-43, solverops_levels_sgs.cpp:37-41
+			P.ytemp.alloc(A.dim());
+			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
+			if(P.uses_levels) build_levels(A, P.levels, P.s.level_mode, st);
+		}
+	}
+	else if(P.is_ilu) {
+		if(first) {
+			// setup_storage + compute_ILU_positions_CSR_CSR on first call: solverops_ilu0.cpp:190-196,358-363
+			P.ilu.alloc((size_t)A.nnzb*A.bs*A.bs);
+			P.ytemp.alloc(A.dim());
+			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
+			if(P.s.scale) P.scale.alloc(A.dim());
+			P.flag.alloc(1);
+			// levels first, as Async_Level_*::compute does (solverops_levels_ilu0.cpp:52-56,139-145)
+			if(P.uses_levels || !P.threadedapply)
+				build_levels(A, P.levels, P.uses_levels ? P.s.level_mode : B200_LEVELS_DAG, st);
+			build_ilu_pattern(A, P.pl, st);
+			// the reference copies A into iluvals at allocation (solverops_ilu0.cpp:160-164,333-337);
+			// this is what INIT_F_NONE then starts from
+			B200_CUDA(cudaMemcpyAsync(P.ilu, A.vals, (size_t)A.nnzb*A.bs*A.bs*sizeof(double),
+			                          cudaMemcpyDeviceToDevice, st));
+			B200_CUDA(cudaEventRecord(P.ev0, st));      // time the factorisation proper
+		}
+		const double *scale = nullptr;
+		if(P.s.scale) {
+			launch_scaling_vector(A, P.scale, st);
+			scale = P.scale;
+		}
+		launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, st);
+
+		// Async_Level_ILU0 (scalar) passes `threadedfactor`=true into the compute_info slot
+		// (solverops_levels_ilu0.cpp:129-130): it always gathers PrecInfo.  Replicated.
+		const bool info = P.s.compute_precinfo ||
+			(type == B200_ASYNC_LEVEL_ILU0 && A.bs == 1);
+		if(info && precinfo)
+			precinfo[1] = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+
+		if(P.threadedfactor) {
+			for(int sw = 0; sw < P.s.nbuildsweeps; sw++)
+				launch_ilu0_sweep(A, P.pl, scale, P.ilu, nullptr, st);
+			P.factor_sweeps_done = P.s.nbuildsweeps;
+		}
+		else if(P.s.nbuildsweeps > 0) {
+			// exact factorisation: iterate to the bitwise fixed point
+			int changed = 1, sw = 0;
+			const int maxsw = A.nbrows*2 + 16;
+			while(changed && sw < maxsw) {
+				B200_CUDA(cudaMemsetAsync(P.flag, 0, sizeof(int), st));
+				for(int rep = 0; rep < 4; rep++, sw++)
+					launch_ilu0_sweep(A, P.pl, scale, P.ilu, P.flag, st);
+				B200_CUDA(cudaMemcpyAsync(&changed, P.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+				B200_CUDA(cudaStreamSynchronize(st));
+			}
+			P.factor_sweeps_done = sw;
+		}
+
+		if(info && precinfo) {
+			precinfo[0] = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+			double dd[4];
+			diag_dominance(A, P.ilu, dd, P.scratch, st);
+			// PrecInfo layout: [2] upper min, [3] upper avg, [4] lower min, [5] lower avg
+			// (preconditioner_diagnostics.hpp:20-30; arr = {lavg, lmin, uavg, umin})
+			precinfo[5] = dd[0]; precinfo[4] = dd[1]; precinfo[3] = dd[2]; precinfo[2] = dd[3];
+		}
+
+		// invert diagonal blocks in place: async_blockilu_factor.cpp:144-146
+		if(A.bs > 1)
+			launch_invert_diag_blocks(A, P.ilu, A.diagind, P.ilu, false, st);
+	}
+	else throw Error("Invalid preconditioner!");
+
+	B200_CUDA(cudaEventRecord(P.ev1, st));
+	P.compute_ms = elapsed(P);
+	P.computed = true;
+}
+
+// ------------------------------------------------------------------ level-scheduled sweeps
+
+static void level_sweep(Prec& P, TriKind kind, TriArgs a, bool backward)
+{
+	const Mat& A = *P.A;
+	const Levels& lv = P.levels;
+	a.rows = (lv.mode == B200_LEVELS_DAG) ? lv.level_rows.p : nullptr;
+	a.descending = backward;
+	if(!backward)
+		for(int l = 0; l < lv.nlevels; l++) {
+			a.row_begin = lv.level_ptr[l]; a.row_end = lv.level_ptr[l+1];
+			launch_tri_sweep(A, kind, a, P.stream);
+		}
+	else
+		for(int l = lv.nlevels-1; l >= 0; l--) {
+			a.row_begin = lv.level_ptr[l]; a.row_end = lv.level_ptr[l+1];
+			launch_tri_sweep(A, kind, a, P.stream);
+		}
+}
+
+// ------------------------------------------------------------------ apply
+
+void prec_apply(Prec& P, const double *r, double *z)
+{
+	Mat& A = *P.A;
+	cudaStream_t st = P.stream;
+	const int type = P.s.prectype;
+	const long long n = A.dim();
+	ensure_events(P);
+	if(type != B200_NO_PREC && !P.computed) throw Error("apply() called before compute()");
+	B200_CUDA(cudaEventRecord(P.ev0, st));
+
+	if(type == B200_NO_PREC) {
+		// NoPreconditioner::apply, solverops_base.cpp:33-38
+		if(r != z) B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+	}
+	else if(type == B200_JACOBI) {
+		launch_jacobi_apply(A, P.dinv, r, z, st);
+	}
+	else if(type == B200_GS) {
+		// ChaoticRelaxation::apply, relaxation_chaotic.cpp:22-45,92-106: forward sweeps in place on
+		// whatever z holds on entry
+		TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.rhs = r; a.x = z;
+		a.row_begin = 0; a.row_end = A.nbrows;
+		for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_RELAX, a, st);
+	}
+	else if(type == B200_SGS) {
+		// AsyncSGS_SRPreconditioner::apply, solverops_sgs.cpp:48-83,148-177
+		const int ai = P.s.apply_inittype;
+		if(ai == B200_INIT_A_JACOBI || ai == B200_INIT_A_ZERO)
+			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
+		TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.row_begin = 0; a.row_end = A.nbrows;
+		a.rhs = r; a.x = P.ytemp; a.descending = false;
+		for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_SGS_FWD, a, st);
+		if(ai == B200_INIT_A_JACOBI)
+			B200_CUDA(cudaMemcpyAsync(z, P.ytemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+		else if(ai == B200_INIT_A_ZERO)
+			B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
+		a.rhs = P.ytemp; a.x = z; a.descending = true;
+		for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_SGS_BWD, a, st);
+	}
+	else if(type == B200_LEVEL_SGS) {
+		// Level_SGS::apply, solverops_levels_sgs.cpp:54-87,160-189
+		TriArgs a; a.vals = A.vals; a.dinv = P.dinv;
+		a.rhs = r; a.x = P.ytemp;
+		level_sweep(P, TRI_SGS_FWD, a, false);
+		a.rhs = P.ytemp; a.x = z;
+		level_sweep(P, TRI_SGS_BWD, a, true);
+	}
+	else if(P.is_ilu) {
+		const double *scale = P.s.scale ? P.scale.p : nullptr;
+		const bool levelled = P.uses_levels || !P.threadedapply;
+		TriArgs a; a.vals = P.ilu; a.row_begin = 0; a.row_end = A.nbrows;
+		if(levelled) {
+			// Async_Level_ILU0::apply (solverops_levels_ilu0.cpp:58-105,148-192), and the exact
+			// triangular solves of the sequential variants
+			if(!P.uses_levels && P.s.apply_inittype == B200_INIT_A_NONE)
+				throw Error(" scalar_ilu0_apply: Invalid init type!");
+			a.rhs = r; a.rscale = scale; a.x = P.ytemp;
+			level_sweep(P, TRI_ILU_LOWER, a, false);
+			a.rhs = P.ytemp; a.rscale = nullptr; a.x = z;
+			level_sweep(P, TRI_ILU_UPPER, a, true);
+		}
+		else {
+			// scalar_ilu0_apply / block_ilu0_apply, solverops_ilu0.cpp:56-148,240-321.
+			// z := S r is folded into the L sweep (rhs scaled on the fly).
+			const int ai = P.s.apply_inittype;
+			if(ai == B200_INIT_A_NONE) throw Error(" scalar_ilu0_apply: Invalid init type!");
+			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
+			a.rhs = r; a.rscale = scale; a.x = P.ytemp; a.descending = false;
+			for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_ILU_LOWER, a, st);
+			if(ai == B200_INIT_A_JACOBI)
+				B200_CUDA(cudaMemcpyAsync(z, P.ytemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+			else
+				B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
+			a.rhs = P.ytemp; a.rscale = nullptr; a.x = z; a.descending = true;
+			for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_ILU_UPPER, a, st);
+		}
+		if(scale) launch_vec_scale_copy(n, scale, z, z, st);      // z := S z
+	}
+	else throw Error("Invalid preconditioner!");
+
+	B200_CUDA(cudaEventRecord(P.ev1, st));
+}
+
+// ------------------------------------------------------------------ relaxation
+
+void prec_apply_relax(Prec& P, const double *b, double *x, int maxits)
+{
+	Mat& A = *P.A;
+	cudaStream_t st = P.stream;
+	const int type = P.s.prectype;
+	const long long n = A.dim();
+	if(type == B200_NO_PREC) return;                      // NoPreconditioner::apply_relax: nothing
+	if(P.is_ilu) throw Error("ILU relaxation not implemented!");   // solverops_ilu0.cpp:215,382
+	if(!P.computed) throw Error("apply_relax() called before compute()");
+
+	TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.rhs = b; a.x = x;
+	a.row_begin = 0; a.row_end = A.nbrows;
+	if(type == B200_JACOBI) {
+		// solverops_jacobi.cpp:66-121,174-220 with ctol == false (what relax_local_blasted sets,
+		// blasted_petsc.cpp:532): xtemp = relax(x); x = xtemp
+		if(!P.xtemp.p) P.xtemp.alloc(n);
+		for(int step = 0; step < maxits; step++) {
+			a.x = P.xtemp; a.xsrc = x;
+			launch_tri_sweep(A, TRI_RELAX, a, st);
+			B200_CUDA(cudaMemcpyAsync(x, P.xtemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+		}
+	}
+	else if(type == B200_GS) {
+		for(int step = 0; step < maxits; step++) launch_tri_sweep(A, TRI_RELAX, a, st);
+	}
+	else if(type == B200_SGS) {
+		// solverops_sgs.cpp:86-116,180-203
+		for(int step = 0; step < maxits; step++) {
+			a.descending = false; launch_tri_sweep(A, TRI_RELAX, a, st);
+			a.descending = true;  launch_tri_sweep(A, TRI_RELAX, a, st);
+		}
+	}
+	else if(type == B200_LEVEL_SGS) {
+		// solverops_levels_sgs.cpp:90-126,192-221
+		for(int step = 0; step < maxits; step++) {
+			level_sweep(P, TRI_RELAX, a, false);
+			level_sweep(P, TRI_RELAX, a, true);
+		}
+	}
+	else throw Error("Invalid preconditioner!");
+}
+
+}  // namespace b200

@@ -1,0 +1,135 @@
+/** \file spmv.cu
+ * \brief CSR / BSR sparse matrix-vector products (K9): y = A x and z = a A x + b y.
+ *
+ * Replaces BLAS_CSR::matrix_apply / gemv3 and BLAS_BSR::matrix_apply / gemv3
+ * (src/blas/matvecs.cpp:25-108 of the reference; `omp parallel for` over rows).
+ *
+ * HBM-bound: algorithmic bytes  CSR 12 nnz + 4(N+1) + 16 N ; BSR (8 b^2 + 4) nnzb + 4(N+1) + 16 b N
+ * (SURVEY.md section 8(d)).  Mapping:
+ *  - CSR: a group of LPR lanes (2..32, chosen from the mean row length) per row; consecutive groups
+ *    take consecutive rows, so a warp's loads of vals/bcolind cover one contiguous span; partial
+ *    sums are combined with warp shuffles.
+ *  - BSR: a group of bs lanes per block-row, lane r owns row r of every block: the group reads
+ *    each column of a (column-major) block as one contiguous bs*8-byte segment, the x segment is a
+ *    broadcast load, no shuffles are needed and the bs results are written contiguously.
+ */
+#include "common.cuh"
+
+namespace b200 {
+
+template <int LPR, bool G3>
+__global__ void __launch_bounds__(256)
+csr_spmv_kernel(const int nrows, const int *__restrict__ rowptr, const int *__restrict__ colind,
+                const double *__restrict__ vals, const double *__restrict__ x,
+                const double a, const double b, const double *yin, double *z)
+{
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	const int row = (int)(tid / LPR);
+	const int lane = (int)(tid % LPR);
+	double sum = 0;
+	if(row < nrows) {
+		const int s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+		for(int j = s + lane; j < e; j += LPR)
+			sum += __ldg(vals + j) * __ldg(x + __ldg(colind + j));
+	}
+#pragma unroll
+	for(int off = LPR/2; off > 0; off >>= 1)
+		sum += __shfl_down_sync(0xffffffffu, sum, off, LPR);
+	if(lane == 0 && row < nrows) {
+		if(G3) z[row] = a*sum + b*yin[row];
+		else z[row] = sum;
+	}
+}
+
+template <int BS, bool G3>
+__global__ void __launch_bounds__(256)
+bsr_spmv_kernel(const int nbrows, const int *__restrict__ browptr, const int *__restrict__ bcolind,
+                const double *__restrict__ vals, const double *__restrict__ x,
+                const double a, const double b, const double *yin, double *z)
+{
+	constexpr int GPW = 32/BS;                     // block-rows per warp
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long rowl = warp*GPW + g;
+	if(g >= GPW || rowl >= nbrows) return;
+	const int row = (int)rowl;
+
+	const int s = __ldg(browptr + row), e = __ldg(browptr + row + 1);
+	double acc = 0;
+#pragma unroll 2
+	for(int jj = s; jj < e; jj++) {
+		const int col = __ldg(bcolind + jj);
+		const double *blk = vals + (size_t)jj*(BS*BS) + r;
+		const double *xs = x + (size_t)col*BS;
+		double av[BS], xv[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) av[c] = __ldg(blk + c*BS);
+#pragma unroll
+		for(int c = 0; c < BS; c++) xv[c] = __ldg(xs + c);
+#pragma unroll
+		for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+	}
+	const size_t o = (size_t)row*BS + r;
+	if(G3) z[o] = a*acc + b*yin[o];
+	else z[o] = acc;
+}
+
+template <bool G3>
+static void launch_csr(const Mat& A, double a, const double *x, double b, const double *y, double *z,
+                       cudaStream_t st)
+{
+	const int n = A.nbrows;
+	const double avg = A.avg_row_len;
+#define B200_CSR_CASE(L)                                                                           \
+	{                                                                                              \
+		const int grid = div_up((long long)n*L, 256);                                              \
+		csr_spmv_kernel<L,G3><<<grid, 256, 0, st>>>(n, A.browptr, A.bcolind, A.vals, x, a, b, y, z); \
+	}
+	if(avg <= 2.5) B200_CSR_CASE(2)
+	else if(avg <= 5) B200_CSR_CASE(4)
+	else if(avg <= 12) B200_CSR_CASE(8)
+	else if(avg <= 24) B200_CSR_CASE(16)
+	else B200_CSR_CASE(32)
+#undef B200_CSR_CASE
+	B200_LAUNCHED();
+}
+
+template <int BS, bool G3>
+static void launch_bsr(const Mat& A, double a, const double *x, double b, const double *y, double *z,
+                       cudaStream_t st)
+{
+	constexpr int GPW = 32/BS;
+	const long long nwarps = ((long long)A.nbrows + GPW - 1)/GPW;
+	const int grid = div_up(nwarps*32, 256);
+	bsr_spmv_kernel<BS,G3><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
+	B200_LAUNCHED();
+}
+
+template <bool G3>
+static void dispatch(const Mat& A, double a, const double *x, double b, const double *y, double *z,
+                     cudaStream_t st)
+{
+	if(A.nbrows == 0) return;
+	switch(A.bs) {
+	case 1: launch_csr<G3>(A, a, x, b, y, z, st); break;
+	case 3: launch_bsr<3,G3>(A, a, x, b, y, z, st); break;
+	case 4: launch_bsr<4,G3>(A, a, x, b, y, z, st); break;
+	case 5: launch_bsr<5,G3>(A, a, x, b, y, z, st); break;
+	case 7: launch_bsr<7,G3>(A, a, x, b, y, z, st); break;
+	default: throw Error("SpMV: block size " + std::to_string(A.bs) + " not supported");
+	}
+}
+
+void launch_spmv(const Mat& A, const double *x, double *y, cudaStream_t st)
+{
+	dispatch<false>(A, 1.0, x, 0.0, nullptr, y, st);
+}
+
+void launch_gemv3(const Mat& A, double a, const double *x, double b, const double *y, double *z,
+                  cudaStream_t st)
+{
+	dispatch<true>(A, a, x, b, y, z, st);
+}
+
+}  // namespace b200

@@ -1,0 +1,197 @@
+/** \file blasted_b200.h
+ * \brief C ABI of the B200-native asynchronous-preconditioner path (libblasted_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Every entry point
+ * names the reference interface it stands in for (paths relative to the BLASTed source tree).
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * blasted_b200/host/b200_solverops.hpp (C++ adapters deriving from the reference's own
+ * SRPreconditioner / FactoryBase classes).
+ *
+ * Conventions
+ *  - all functions return 0 on success, non-zero on failure; b200_last_error() gives the message
+ *    (the C++ adapters re-throw the reference's exception types; nothing throws across this ABI);
+ *  - matrices are square sparse (block-)row matrices in the reference layout
+ *    (include/srmatrixdefs.hpp:38-79): browptr[nbrows+1], bcolind[nnzb] sorted ascending per row,
+ *    vals[nnzb*bs*bs] with contiguous bs x bs blocks, diagind[nbrows]; int32 indices, fp64 values;
+ *  - `*_host` variants take host buffers and perform the H2D/D2H copies themselves (what PETSc's
+ *    PCApply hands over, src/blasted_petsc.cpp:474-517); un-suffixed compute-path variants taking
+ *    `d_` arguments expect device pointers and are asynchronous on the handle's CUDA stream;
+ *  - one in-flight operation per handle (the reference objects are not re-entrant either:
+ *    `apply` mutates the shared scratch `ytemp`, src/solverops_ilu0.cpp:280).
+ *  - There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef BLASTED_B200_H
+#define BLASTED_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums: numeric values identical to the reference ---- */
+
+/** include/solvertypes.h:14-26 (BlastedSolverType) */
+typedef enum {
+	B200_JACOBI = 0,
+	B200_GS = 1,
+	B200_SGS = 2,
+	B200_ILU0 = 3,
+	B200_SEQILU0 = 4,
+	B200_SFILU0 = 5,
+	B200_SAPILU0 = 6,
+	B200_CSC_BGS = 7,          /* not provided (out of scope: solverops_sgs.hpp:116-119) */
+	B200_LEVEL_SGS = 8,
+	B200_ASYNC_LEVEL_ILU0 = 9,
+	B200_NO_PREC = 10,
+	B200_EXTERNAL = 11         /* not provided */
+} b200_solver_type;
+
+/** include/async_initialization_decl.hpp:16-25 (FactInit) */
+typedef enum { B200_INIT_F_ZERO = 0, B200_INIT_F_ORIGINAL = 1, B200_INIT_F_SGS = 2,
+               B200_INIT_F_NONE = 3 } b200_fact_init;
+/** include/async_initialization_decl.hpp:28-35 (ApplyInit) */
+typedef enum { B200_INIT_A_ZERO = 0, B200_INIT_A_JACOBI = 1, B200_INIT_A_NONE = 2 } b200_apply_init;
+
+/** Block layout: Eigen::ColMajor = 0, Eigen::RowMajor = 1 (include/blasted_config.hpp:13-14) */
+typedef enum { B200_COLMAJOR = 0, B200_ROWMAJOR = 1 } b200_block_storage;
+
+/** How the level-scheduled objects order rows (device-side choice; no reference counterpart).
+ *  CONTIGUOUS reproduces src/levelschedule.cpp:12-71 bit-for-bit (levels of consecutive rows);
+ *  DAG uses true dependency wavefronts (same numerical result: exact substitution). */
+typedef enum { B200_LEVELS_DAG = 0, B200_LEVELS_CONTIGUOUS = 1 } b200_level_mode;
+
+/** Mirrors AsyncSolverSettings : SolverSettings (include/solverfactory.hpp:46-68). */
+typedef struct b200_settings {
+	int prectype;             /* b200_solver_type */
+	int bs;                   /* block size: 1, 4 or 5 (preconditioners); SpMV also 3 and 7 */
+	int blockstorage;         /* b200_block_storage */
+	int relax;                /* request relaxation instead of preconditioning */
+	int thread_chunk_size;    /* (block-)rows per CTA hint; <= 0 selects the default */
+	int scale;                /* symmetric scaling of the matrix before ILU */
+	int nbuildsweeps;         /* asynchronous factorisation sweeps */
+	int napplysweeps;         /* asynchronous triangular-solve / SGS sweeps */
+	int fact_inittype;        /* b200_fact_init */
+	int apply_inittype;       /* b200_apply_init */
+	int compute_precinfo;     /* fill the 6-entry PrecInfo in b200_prec_compute */
+	int level_mode;           /* b200_level_mode, for the level-scheduled types */
+} b200_settings;
+
+typedef struct b200_mat b200_mat;       /* device-resident CSR/BSR matrix (operator A) */
+typedef struct b200_prec b200_prec;     /* preconditioner object */
+
+/* ---- library ---- */
+const char *b200_last_error(void);
+/** Number of CUDA devices visible, 0 if none (never fails). */
+int b200_device_count(void);
+/** Select the device used by handles created afterwards on this thread (cudaSetDevice). */
+int b200_set_device(int device);
+/** Number of kernels launched by this library since load / the last reset (bench evidence). */
+long long b200_kernel_launches(void);
+void b200_reset_kernel_launches(void);
+
+/* ---- device-resident matrix: SRMatrixStorage + CSRMatrixView/BSRMatrixView
+ *      (include/srmatrixdefs.hpp:38-79, include/blockmatrices.hpp:71-160) ---- */
+
+/** Copies a host matrix to the device.  Stands in for wrapping raw arrays in
+ *  SRMatrixStorage<const double,const int> (src/blasted_petsc.cpp:285-297) plus
+ *  CSRMatrixView/BSRMatrixView construction (tests/testsolve.cpp:43-56).
+ *  diagind may be NULL (it is then located on the device); a missing diagonal is only an error
+ *  for preconditioners, not for SpMV. */
+int b200_mat_create_host(int nbrows, int bs, int blockstorage, const int *browptr,
+                         const int *bcolind, const double *vals, const int *diagind,
+                         b200_mat **out);
+/** Same, from device arrays that are copied (pattern) / transposed-or-copied (values). */
+int b200_mat_create_device(int nbrows, int bs, int blockstorage, const int *d_browptr,
+                           const int *d_bcolind, const double *d_vals, b200_mat **out);
+/** New values on the same pattern (PETSc rewrites `a` in place between solves,
+ *  include/solverops_ilu0.hpp:53-56). */
+int b200_mat_update_values_host(b200_mat *m, const double *vals);
+int b200_mat_update_values_device(b200_mat *m, const double *d_vals);
+void b200_mat_destroy(b200_mat *m);
+int b200_mat_dim(const b200_mat *m);            /* nbrows*bs, as MatrixView::dim() */
+int b200_mat_nbrows(const b200_mat *m);
+long long b200_mat_nnzb(const b200_mat *m);
+int b200_mat_set_stream(b200_mat *m, void *cuda_stream);
+
+/** y = A x  : AbstractLinearOperator::apply (include/linearoperator.hpp:36),
+ *  BLAS_CSR/BLAS_BSR::matrix_apply (src/blas/matvecs.cpp:25-48, 78-91). */
+int b200_mat_apply(const b200_mat *m, const double *d_x, double *d_y);
+int b200_mat_apply_host(const b200_mat *m, const double *x, double *y);
+/** z = a A x + b y : MatrixView::gemv3 (include/linearoperator.hpp:125-131, matvecs.cpp:51-108). */
+int b200_mat_gemv3(const b200_mat *m, double a, const double *d_x, double b, const double *d_y,
+                   double *d_z);
+int b200_mat_gemv3_host(const b200_mat *m, double a, const double *x, double b, const double *y,
+                        double *z);
+
+/* ---- preconditioners: SRFactory::create_preconditioner + Preconditioner virtuals
+ *      (src/solverfactory.cpp:131-228, include/solverops_base.hpp:32-64) ---- */
+
+/** Creates the preconditioner of settings->prectype on the matrix `m` (shared, not copied; `m`
+ *  must outlive the preconditioner).  Fails for invalid (prectype, bs, blockstorage) combinations
+ *  exactly where the reference throws std::invalid_argument (src/solverfactory.cpp:122, 203-206,
+ *  220-227); b200_last_error() carries the reference's message. */
+int b200_prec_create(const b200_settings *settings, b200_mat *m, b200_prec **out);
+/** Preconditioner::compute(): (re)build from the matrix's current values; first call also builds
+ *  the ILU position lists / level schedule on the device (src/solverops_ilu0.cpp:190-202,358-368).
+ *  precinfo may be NULL; layout = PrecInfo::f_info (include/preconditioner_diagnostics.hpp:14-58). */
+int b200_prec_compute(b200_prec *p, double precinfo[6]);
+/** Preconditioner::apply(r, z) : z = M^-1 r. */
+int b200_prec_apply(b200_prec *p, const double *d_r, double *d_z);
+int b200_prec_apply_host(b200_prec *p, const double *r, double *z);
+/** setApplyParams({.., maxits}) + apply_relax(b, x) (src/blasted_petsc.cpp:519-576): x is
+ *  updated in place.  Fails with the reference's message where it throws
+ *  ("ILU relaxation not implemented!", src/solverops_ilu0.cpp:215). */
+int b200_prec_apply_relax(b200_prec *p, const double *d_b, double *d_x, int maxits);
+int b200_prec_apply_relax_host(b200_prec *p, const double *b, double *x, int maxits);
+int b200_prec_dim(const b200_prec *p);
+int b200_prec_relaxation_available(const b200_prec *p);
+void b200_prec_destroy(b200_prec *p);
+int b200_prec_set_stream(b200_prec *p, void *cuda_stream);
+/** Change sweep counts after creation (bench / convergence studies). */
+int b200_prec_set_sweeps(b200_prec *p, int nbuildsweeps, int napplysweeps);
+
+/* ---- setup products and diagnostics, for parity checks ---- */
+
+/** ILUPositions (include/ilu_pattern.hpp:36-48) built on the device: sizes, then copy-out. */
+int b200_prec_positions_size(b200_prec *p, long long *npos);
+int b200_prec_get_positions(b200_prec *p, int *posptr, int *lowerp, int *upperp);
+/** Level schedule.  CONTIGUOUS mode: `levels` (nlevels+1 entries) as computeLevels returns.
+ *  DAG mode: level pointers (nlevels+1) and the row list ordered by level (nbrows). */
+int b200_prec_levels_size(b200_prec *p, int *nlevels);
+int b200_prec_get_levels(b200_prec *p, int *level_ptr, int *level_rows_or_null);
+/** Factor values in the caller's block layout; diagonal blocks inverted for bs > 1, exactly what
+ *  the reference holds in `iluvals` after compute() (src/async_blockilu_factor.cpp:144-146). */
+int b200_prec_get_factor(b200_prec *p, double *iluvals);
+/** Inverted diagonal (blocks) of the Jacobi-derived objects (`dblocks`, solverops_jacobi.cpp:31). */
+int b200_prec_get_dblocks(b200_prec *p, double *dblocks);
+/** Symmetric scaling vector (src/rawsrmatrixutils.cpp:343-350), if scaling is on. */
+int b200_prec_get_scale(b200_prec *p, double *scale);
+/** sum |(A - LU)_S| of the current factor (src/async_ilu_factor.cpp:180-217,
+ *  src/async_blockilu_factor.cpp:257-297).  Valid for ILU0-type objects after compute(). */
+int b200_prec_ilu_residual(b200_prec *p, double *res);
+/** Device time (ms, CUDA events) of the last compute() and the last apply() on this handle:
+ *  the device-side counterpart of Blasted_data.{factor,apply}walltime (include/blasted_petsc.h:31-64). */
+int b200_prec_last_times(b200_prec *p, double *compute_ms, double *apply_ms);
+
+/* ---- Krylov test drivers on the device (tests/solvers.cpp:90-352) ---- */
+
+typedef struct b200_solve_info {
+	int converged;
+	int iters;            /* as SolveInfo::iters: BiCGSTAB step+1, GCR/Richardson step */
+	double resnorm;       /* 2-norm of the final residual */
+	double bnorm;         /* 2-norm of the right-hand side */
+	double device_ms;     /* CUDA-event time of the whole solve */
+	double prec_ms;       /* of which preconditioner applications */
+} b200_solve_info;
+
+/** solver: "bicgstab" (tests/solvers.cpp:140-244), "gcr" (:252-352, == FGMRES in exact
+ *  arithmetic, tests/solvers.hpp:108-110), "richardson" (:90-133).  Host b/x. */
+int b200_solve_host(const char *solver, const b200_mat *A, b200_prec *M, const double *b, double *x,
+                    double tol, int maxiter, int restart, b200_solve_info *info);
+/** Device b/x. */
+int b200_solve(const char *solver, const b200_mat *A, b200_prec *M, const double *d_b, double *d_x,
+               double tol, int maxiter, int restart, b200_solve_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,60 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header declares,
+and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "blasted_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from blasted_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/blasted_b200.h but not exported"
+    # and the Python binding table covers the header exactly
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_no_oracle_in_product_path():
+    """The product never links or imports the oracle."""
+    pkg = os.path.join(ROOT, "blasted_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "blasted_oracle" not in txt
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M)
+
+
+def test_compute_fails_loudly_without_gpu():
+    import blasted_b200 as bb
+    if bb.device_count() > 0:
+        pytest.skip("GPU present")
+    m = bb.matgen.poisson3d(3)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        bb.CSRMatrixView(m)
+
+
+def test_settings_struct_layout():
+    from blasted_b200 import _lib
+    assert ctypes.sizeof(_lib.Settings) == 12*4
+    assert ctypes.sizeof(_lib.SolveInfo) == 2*4 + 4*8
+
+
+def test_factory_strings():
+    import blasted_b200 as bb
+    f = bb.SRFactory()
+    assert f.solverTypeFromString("ilu0") == 3 and f.solverTypeFromString("none") == 10
+    with pytest.raises(ValueError):
+        f.solverTypeFromString("bogus")

@@ -1,0 +1,64 @@
+"""GPU property tests at BASELINE.json's full sizes (C2: BSR4 1024x1024 cells; C1-class Poisson),
+where the CPU oracle is too slow for an element-wise comparison: size-independent properties."""
+import numpy as np
+import pytest
+
+import blasted_b200 as bb
+from blasted_b200 import matgen
+from blasted_b200.solverfactory import SOLVER_TYPES
+from util import relerr, SEED
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_bsr4_factor_apply_properties():
+    import torch
+    m = matgen.block_stencil((1024, 1024), 4, SEED + 2)
+    assert m.nbrows == 1048576
+    view = bb.SRMatrixView(m)
+    # SpMV: A*1 equals the host row sums
+    ones = np.ones(m.dim)
+    rows = np.repeat(np.arange(m.nbrows), np.diff(m.browptr))
+    blocks = m.vals.reshape(-1, 4, 4)               # column-major blocks: [c, r]
+    rs = np.zeros((m.nbrows, 4))
+    np.add.at(rs, rows, blocks.sum(axis=1))
+    assert relerr(view.apply(ones), rs.ravel()) < 1e-12
+
+    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["ilu0"], bs=4, nbuildsweeps=1, napplysweeps=1,
+                               compute_precinfo=True)
+    p = bb.SRFactory().create_preconditioner(view, s)
+    res = []
+    for nsw in (1, 2, 4, 8):
+        p.set_sweeps(nsw, 1)
+        info = p.compute().f_info
+        res.append(info[0]/info[1])
+    assert res[0] < 1.0 and res[-1] < 1e-10 and all(b <= a*1.0001 for a, b in zip(res, res[1:]))
+
+    # apply: with converged sweeps M^-1 = (LU)^-1; then ||A z - r|| << ||r|| for this
+    # diagonally dominant matrix, and applying is linear
+    p.set_sweeps(8, 12)
+    p.compute()
+    rng = np.random.default_rng(SEED)
+    r1, r2 = rng.standard_normal(m.dim), rng.standard_normal(m.dim)
+    z1, z2, z12 = p.apply(r1), p.apply(r2), p.apply(r1 - 2.0*r2)
+    assert relerr(z12, z1 - 2.0*z2) < 1e-9
+    assert np.linalg.norm(view.apply(z1) - r1) < 0.05*np.linalg.norm(r1)
+
+
+def test_poisson128_exact_vs_async_solve():
+    m = matgen.poisson3d(128)
+    view = bb.SRMatrixView(m)
+    b = view.apply(np.ones(m.dim))
+    its = {}
+    for ptype, kw in (("sapilu0", dict(nbuildsweeps=20)), ("ilu0", dict(nbuildsweeps=20, napplysweeps=40))):
+        p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+            prectype=SOLVER_TYPES[ptype], bs=1, **kw))
+        p.compute()
+        sol = bb.BiCGSTAB(view, p)
+        sol.setParams(1e-8, 1000)
+        x = np.zeros(m.dim)
+        info = sol.solve(b, x)
+        assert info.resnorm/info.bnorm < 1e-8
+        assert relerr(x, np.ones(m.dim)) < 1e-5
+        its[ptype] = info.iters
+    assert abs(its["ilu0"] - its["sapilu0"]) <= max(1, int(np.ceil(0.05*its["sapilu0"])))
