@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py - async block-ILU(0) factor + apply throughput on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref)
+
+Workload (config.workload = "C2"): synthetic 2D compressible-flow-like BSR bs=4 Jacobian, 1024x1024
+cells = 1 048 576 block rows, 5-point block stencil (BASELINE.json configs[1]).
+One STEP = compute() [init + nbuild async block-ILU(0) sweeps + diagonal-block inversion] followed by
+apply() [napply async lower + upper block-triangular sweeps], sweeps (3,3).
+metric = algorithmic HBM bytes moved by one step / time ("async ILU factor+apply HBM GB/s").
+At N > 1 every rank factors and applies its own subdomain of the same size (block-Jacobi: the
+preconditioner needs no communication) -> weak scaling, value = bytes of all ranks / max time.
+See DESIGN.md section "Measurement" for the byte formulas.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20261018 + 2
+NBUILD, NAPPLY = 3, 3
+
+
+# ----------------------------------------------------------------------------- workload + bytes
+
+def make_matrix(rank, cells):
+    from blasted_b200 import matgen
+    return matgen.block_stencil((cells, cells), 4, SEED + 1000*rank)
+
+
+def algorithmic_bytes(m, npos, nbuild, napply):
+    """Compulsory HBM traffic of one step (int32 = 4 B, fp64 = 8 B)."""
+    b, N, nnz = m.bs, m.nbrows, m.nnzb
+    b2 = b*b
+    sweep = nnz*(24*b2 + 8) + 8*npos + 8*N              # read A, read+write factor, pattern
+    init = nnz*16*b2                                     # read A, write factor
+    dinv = 16*b2*N + 4*N                                 # diagonal block inversion
+    apply_pair = (8*b2 + 4)*nnz + 12*N + 48*b*N          # factor + indices once, vectors
+    return {"factor_sweep": sweep, "init": init, "diag_invert": dinv, "apply_pair": apply_pair,
+            "step": init + nbuild*sweep + dinv + napply*apply_pair}
+
+
+def kernel_bytes(m, npos, nlower, nupper):
+    """Algorithmic bytes of ONE launch of each kernel class."""
+    b, N, nnz = m.bs, m.nbrows, m.nnzb
+    b2 = b*b
+    # lower launch: A read + factor write per lower entry, U_jj^-1 read once per block column, list
+    lower = nlower*(16*b2 + 8 + 8) + 8*b2*N
+    # upper launch: A read + factor write per upper entry, two partner blocks per product,
+    # refreshed inverse per row, lists
+    upper = nupper*(16*b2 + 16) + npos*(16*b2 + 8) + 8*b2*N
+    nl_apply = nlower*(8*b2 + 4) + 8*N + 24*b*N          # L sweep: lower blocks, r, y gathered+written
+    nu_apply = nupper*(8*b2 + 4) + 8*N + 24*b*N
+    return {"factor_lower": lower, "factor_upper": upper, "tri_lower": nl_apply, "tri_upper": nu_apply}
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2+i].lower().startswith("active")
+                                                         for s in self.samples if len(s) > 2+i)]
+        mx = self.samples[0][1]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(mx) if mx.replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+
+def cpu_step_time(m, steps, warmup, nbuild, napply):
+    """Times the reference's own OpenMP path (oracle/_ref) or, failing that, the sequential oracle
+    port, on the host cores.  Returns (seconds per step, kind, cores)."""
+    from oracle import have_ref, ref, orc
+    r = np.random.default_rng(SEED).standard_normal(m.dim)
+    if have_ref():
+        R = ref()
+        cores = R.num_threads()
+        p = R.prec(m, "ilu0", nbuildsweeps=nbuild, napplysweeps=napply, thread_chunk_size=128,
+                   fact_init="init_original", apply_init="init_jacobi")
+        p.compute()                       # first call builds the (serial) position lists: not timed
+        ts = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            p.compute()
+            p.apply(r)
+            if it >= warmup:
+                ts.append(time.perf_counter() - t0)
+        p.close()
+        return float(np.mean(ts)), "reference", cores
+    O = orc()
+    plist = O.ilu_positions(m)
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ilu = O.ilu0_init(m, None, "init_original")
+        O.ilu0_sweeps(m, plist, None, nbuild, ilu)
+        O.ilu0_invert_diag(m, ilu)
+        O.ilu0_apply(m, ilu, None, napply, "init_jacobi", r)
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), "port", 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # rank 0 alone runs the CPU arm
+    cells = args.cells
+    m = make_matrix(0, cells)
+    from oracle import orc
+    npos = len(orc().ilu_positions(m)[1]) if cells <= 256 else 2*(cells*cells) - 2*cells
+    by = algorithmic_bytes(m, npos, NBUILD, NAPPLY)
+    sec, kind, cores = cpu_step_time(m, args.steps, min(args.warmup, 1), NBUILD, NAPPLY)
+    val = by["step"]/sec/1e9
+    line = {"impl": "reference", "metric": "async_ilu0_factor_apply_hbm_gbs", "value": val,
+            "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": sec*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(m, cells),
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind,
+                             "sample": f"full C2 step ({NBUILD} factor sweeps + {NAPPLY} apply sweep "
+                                       f"pairs) x {args.steps} on the host cores"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(m, cells):
+    return {"workload": "C2", "matrix": f"synthetic BSR bs=4 5-point block stencil, {cells}x{cells} cells",
+            "block_rows": m.nbrows, "nnzb": m.nnzb, "prectype": "ilu0 (async block-ILU(0))",
+            "nbuildsweeps": NBUILD, "napplysweeps": NAPPLY, "fact_init": "init_original",
+            "apply_init": "init_jacobi", "parallelism": "one subdomain per GPU (block-Jacobi)",
+            "l2_policy": "inputs larger than L2 (matrix+factor 1.3 GB vs 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------- our arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import blasted_b200 as bb
+    from blasted_b200 import solverfactory as sf
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if bb.device_count() == 0:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cells = args.cells
+    m = make_matrix(rank, cells)
+    view = bb.SRMatrixView(m)
+    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=4, nbuildsweeps=NBUILD,
+                               napplysweeps=NAPPLY)
+    prec = bb.SRFactory().create_preconditioner(view, s)
+    prec.compute()                                        # pattern + first factorisation (setup)
+    posptr, lowerp, _ = prec.ilu_positions()
+    npos = len(lowerp)
+    nlower = int((m.diagind - m.browptr[:-1]).sum())
+    nupper = m.nnzb - nlower
+    by = algorithmic_bytes(m, npos, NBUILD, NAPPLY)
+    kby = kernel_bytes(m, npos, nlower, nupper)
+
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    r_dev = torch.randn(m.dim, dtype=torch.float64, device="cuda", generator=gen)
+    z_dev = torch.empty_like(r_dev)
+
+    def step():
+        prec.compute()
+        prec.apply(r_dev, z_dev)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    sf.profile_reset()
+    sf.profile_enable(True)
+    bb.reset_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = bb.kernel_launches()
+    prof = sf.profile_get()
+    sf.profile_enable(False)
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world*by["step"]*args.steps/(ms_max*1e-3)/1e9
+
+    # ---- end to end through the host-pointer C ABI: new matrix values and r from pinned host
+    # memory every step, z read back to the host every step
+    vals_pin = torch.from_numpy(m.vals).pin_memory()
+    r_pin = r_dev.cpu().pin_memory()
+    z_pin = torch.empty(m.dim, dtype=torch.float64).pin_memory()
+    vals_np, r_np, z_np = vals_pin.numpy(), r_pin.numpy(), z_pin.numpy()
+
+    def step_e2e():
+        view.update_values(vals_np)                       # H2D of the Jacobian values
+        prec.compute()
+        prec.apply(r_np, z_np)                            # H2D r, kernels, D2H z
+
+    esteps = max(1, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        step_e2e()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world*by["step"]*esteps/float(t_e2e.item())/1e9
+    checksum = float(np.abs(z_np).sum())
+    assert np.isfinite(checksum)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the live per-launch CUDA-event times
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kernels = {}
+    for k in ("factor_lower", "factor_upper", "tri_lower", "tri_upper"):
+        tot, cnt = prof[k]
+        if cnt:
+            avg = tot/cnt
+            kernels[k] = {"avg_ms": avg, "launches": cnt, "share_of_step": tot/ms,
+                          "achieved_gbs": kby[k]/(avg*1e-3)/1e9, "bytes_per_launch": kby[k]}
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
+    roofline = None
+    if dom:
+        ach = kernels[dom]["achieved_gbs"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kby[dom]}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only), bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        csteps = 2
+        sec, kind, cores = cpu_step_time(m, csteps, 1, NBUILD, NAPPLY)
+        cpu = {"value": by["step"]/sec/1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+               "ms_per_step": sec*1e3,
+               "sample": f"full C2 step x {csteps} (1 warm-up) on the host cores, same matrix"}
+
+    line = {"metric": "async_ilu0_factor_apply_hbm_gbs", "value": value, "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max/args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(m, cells),
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_val, "unit": "GB/s",
+                    "h2d_bytes_per_step": int(m.vals.nbytes + r_np.nbytes),
+                    "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "algorithmic_bytes_per_step": by["step"], "frac_of_peak_whole_step": value/world/peak}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=1024, help="cells per side (C2 = 1024)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

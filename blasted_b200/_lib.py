@@ -35,6 +35,9 @@ SYMBOLS = {
     "b200_set_device": (_i, [_i]),
     "b200_kernel_launches": (_ll, []),
     "b200_reset_kernel_launches": (None, []),
+    "b200_profile_enable": (None, [_i]),
+    "b200_profile_reset": (None, []),
+    "b200_profile_get": (_i, [_vp, _vp]),
     "b200_mat_create_host": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _pp]),
     "b200_mat_create_device": (_i, [_i, _i, _i, _vp, _vp, _vp, _pp]),
     "b200_mat_update_values_host": (_i, [_vp, _vp]),

@@ -12,6 +12,39 @@ struct b200_prec { b200::Prec p; };
 namespace b200 {
 
 std::atomic<long long> g_launches{0};
+Profiler g_prof;
+
+cudaEvent_t Profiler::get()
+{
+	if(!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+	cudaEvent_t e;
+	B200_CUDA(cudaEventCreate(&e));
+	return e;
+}
+void Profiler::begin(int kc, cudaStream_t st)
+{
+	Rec r; r.a = get(); r.b = get(); r.kc = kc;
+	B200_CUDA(cudaEventRecord(r.a, st));
+	pending.push_back(r);
+}
+void Profiler::end(cudaStream_t st) { B200_CUDA(cudaEventRecord(pending.back().b, st)); }
+void Profiler::collect()
+{
+	for(Rec& r : pending) {
+		float t = 0;
+		if(cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+			ms[r.kc] += t; count[r.kc]++;
+		}
+		pool.push_back(r.a); pool.push_back(r.b);
+	}
+	pending.clear();
+}
+void Profiler::reset()
+{
+	collect();
+	for(int i = 0; i < KC_COUNT; i++) { ms[i] = 0; count[i] = 0; }
+}
+Profiler::~Profiler() { /* events are released with the context */ }
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
@@ -135,6 +168,16 @@ int b200_set_device(int device) { return guarded([&] { B200_CUDA(cudaSetDevice(d
 
 long long b200_kernel_launches(void) { return g_launches.load(); }
 void b200_reset_kernel_launches(void) { g_launches.store(0); }
+
+void b200_profile_enable(int on) { g_prof.enabled = on != 0; }
+void b200_profile_reset(void) { try { g_prof.reset(); } catch(...) {} }
+int b200_profile_get(double ms[8], long long count[8])
+{
+	return guarded([&] {
+		g_prof.collect();
+		for(int i = 0; i < KC_COUNT; i++) { ms[i] = g_prof.ms[i]; count[i] = g_prof.count[i]; }
+	});
+}
 
 // ------------------------------------------------------------------ matrix
 

@@ -184,6 +184,8 @@ void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t
 	d.xsrc = a.xsrc ? a.xsrc : a.x; d.x = a.x; d.rows = a.rows;
 	d.row_begin = a.row_begin; d.row_end = a.row_end; d.descending = a.descending ? 1 : 0;
 	const double half = 0.5*(A.avg_row_len - 1.0);
+	ProfScope ps((kind == TRI_ILU_LOWER || kind == TRI_SGS_FWD) ? KC_TRI_LOWER :
+	             (kind == TRI_ILU_UPPER || kind == TRI_SGS_BWD) ? KC_TRI_UPPER : KC_OTHER, st);
 	switch(kind) {
 	case TRI_ILU_LOWER: launch_kind<TRI_ILU_LOWER>(A, d, half, st); break;
 	case TRI_ILU_UPPER: launch_kind<TRI_ILU_UPPER>(A, d, half, st); break;

@@ -45,6 +45,36 @@ extern std::atomic<long long> g_launches;
 		B200_CUDA(cudaGetLastError());                                                       \
 	} while(0)
 
+// ---------------------------------------------------------------- per-kernel-class timing
+//
+// Optional (off by default): CUDA events around the launches of each kernel class on the launching
+// stream, accumulated on request.  This is what bench.py uses for the live roofline figure.
+
+enum KClass { KC_FACTOR_LOWER = 0, KC_FACTOR_UPPER, KC_FACTOR_INIT, KC_DIAG_INVERT, KC_TRI_LOWER,
+              KC_TRI_UPPER, KC_SPMV, KC_OTHER, KC_COUNT };
+
+struct Profiler {
+	bool enabled = false;
+	struct Rec { cudaEvent_t a, b; int kc; };
+	std::vector<Rec> pending;
+	std::vector<cudaEvent_t> pool;
+	double ms[KC_COUNT] = {0};
+	long long count[KC_COUNT] = {0};
+	cudaEvent_t get();
+	void begin(int kc, cudaStream_t st);
+	void end(cudaStream_t st);
+	void collect();                       ///< synchronises the pending events and accumulates
+	void reset();
+	~Profiler();
+};
+extern Profiler g_prof;
+
+struct ProfScope {
+	cudaStream_t st; bool on;
+	ProfScope(int kc, cudaStream_t s) : st(s), on(g_prof.enabled) { if(on) g_prof.begin(kc, st); }
+	~ProfScope() { if(on) g_prof.end(st); }
+};
+
 // ---------------------------------------------------------------- device buffers
 
 template <typename T>
@@ -104,7 +134,12 @@ int find_diagonals(Mat& A, cudaStream_t st);
 // pattern.cu
 struct IluPattern {
 	long long npos = 0;
-	DevBuf<int> posptr, lowerp, upperp;
+	DevBuf<int> posptr, lowerp, upperp;  ///< the reference's ILUPositions arrays (bit-identical)
+	// packed per-phase work lists for the block kernels (device-side design, built from the above)
+	long long nlower = 0, nupper = 0;
+	DevBuf<int2> lmeta;                  ///< per lower entry: {entry, block-column}
+	DevBuf<int4> umeta;                  ///< per upper entry: {entry, pos begin, pos end, row if diagonal else -1}
+	DevBuf<int2> pairs;                  ///< {lowerp[k], upperp[k]} interleaved
 	bool built = false;
 };
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
@@ -125,7 +160,11 @@ void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *
 /// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
 /// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
-                       int *d_changed, cudaStream_t st);
+                       double *dinv, int *d_changed, cudaStream_t st);
+/// dst[positions[i]] <- src[i] for nbrows blocks (copies the compact inverted diagonal blocks into
+/// the factor, the reference's in-place inversion, async_blockilu_factor.cpp:144-146)
+void launch_scatter_blocks(const Mat& A, const double *src_compact, const int *positions, double *dst,
+                           cudaStream_t st);
 void launch_invert_diag_blocks(const Mat& A, const double *src_vals, const int *positions_or_null,
                                double *dst, bool dst_is_compact, cudaStream_t st);
 double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,

@@ -355,6 +355,262 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 	}
 }
 
+
+// ------------------------------------------------------------------ block ILU(0): sweep kernels
+//
+// The two launches of one sweep.  Work items come from the packed per-phase lists (IluPattern),
+// a persistent grid walks them in ascending order with the metadata of the NEXT item prefetched
+// while the current one is processed, so that only one memory latency (the block loads) is exposed
+// per item instead of the index chain entry -> column -> diagonal position -> block.
+//
+// Lower entry (i,j), i>j:  L_ij = (A_ij - sum_k L_ik U_kj) U_jj^-1.  U_jj^-1 is read from the compact
+// array `dinv`, which the upper launch of the previous sweep (or the initialisation) wrote from the
+// very U_jj the reference would invert here (kernels_ilu0_factorize.hpp:91); during the lower launch
+// nobody writes U_jj, so the value used is the same.
+// Upper entry (i,j), i<=j: U_ij = A_ij - sum_k L_ik U_kj; a diagonal entry also refreshes dinv[i].
+
+template <int BS>
+__device__ __forceinline__ void load_row_strided(const double *p, double (&v)[BS])
+{
+#pragma unroll
+	for(int c = 0; c < BS; c++) v[c] = __ldg(p + c*BS);
+}
+
+template <int BS, bool SCALE>
+__global__ void __launch_bounds__(256)
+block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
+                        const int *__restrict__ browind, const double *__restrict__ avals,
+                        const int *__restrict__ posptr, const int2 *__restrict__ pairs,
+                        const double *__restrict__ scale, const double *__restrict__ dinv,
+                        double *ilu, int *__restrict__ changed)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const long long stride = (((long long)gridDim.x*blockDim.x) >> 5)*GPW;
+	const bool lanevalid = g < GPW;
+
+	long long t = warp*GPW + g;
+	int2 meta = make_int2(-1, -1);
+	if(lanevalid && t < nlower) meta = __ldg(lmeta + t);
+	const long long niter = (nlower + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		const long long tn = t + stride;
+		int2 metan = make_int2(-1, -1);
+		if(lanevalid && tn < nlower) metan = __ldg(lmeta + tn);       // prefetch next item's indices
+
+		if(meta.x >= 0) {
+			const int entry = meta.x, col = meta.y;
+			double sum[BS], di[BS2];
+			load_row_strided<BS>(avals + (size_t)entry*BS2 + r, sum);
+			load_block<BS,false>(dinv + (size_t)col*BS2, di);
+			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
+			if(SCALE) {
+				const int row = __ldg(browind + entry);
+				const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+			}
+			for(int k = ps; k < pe; k++) {
+				const int2 pr = __ldg(pairs + k);
+				const double *lb = ilu + (size_t)pr.x*BS2 + r;
+				double lr[BS], u[BS2];
+#pragma unroll
+				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
+				load_block<BS,true>(ilu + (size_t)pr.y*BS2, u);
+#pragma unroll
+				for(int c = 0; c < BS; c++)
+#pragma unroll
+					for(int m = 0; m < BS; m++)
+						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
+			}
+			double out[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++) {
+				double a = 0;
+#pragma unroll
+				for(int m = 0; m < BS; m++) a = fma(sum[m], di[c*BS+m], a);
+				out[c] = a;
+			}
+			double *op = ilu + (size_t)entry*BS2 + r;
+			if(changed) {
+				bool ch = false;
+#pragma unroll
+				for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != out[c]);
+				if(ch) *changed = 1;
+			}
+#pragma unroll
+			for(int c = 0; c < BS; c++) op[c*BS] = out[c];              // single final store per value
+		}
+		meta = metan;
+		t = tn;
+	}
+}
+
+template <int BS, bool SCALE>
+__global__ void __launch_bounds__(256)
+block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
+                        const int *__restrict__ browind, const int *__restrict__ bcolind,
+                        const double *__restrict__ avals, const int2 *__restrict__ pairs,
+                        const double *__restrict__ scale, double *__restrict__ dinv,
+                        double *ilu, int *__restrict__ changed)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const long long stride = (((long long)gridDim.x*blockDim.x) >> 5)*GPW;
+	const bool lanevalid = g < GPW;
+
+	long long t = warp*GPW + g;
+	int4 meta = make_int4(-1, 0, 0, -1);
+	if(lanevalid && t < nupper) meta = __ldg(umeta + t);
+	const long long niter = (nupper + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		const long long tn = t + stride;
+		int4 metan = make_int4(-1, 0, 0, -1);
+		if(lanevalid && tn < nupper) metan = __ldg(umeta + tn);
+
+		const bool active = meta.x >= 0;
+		const bool isdiag = active && meta.w >= 0;
+		double sum[BS];
+		if(active) {
+			const int entry = meta.x;
+			load_row_strided<BS>(avals + (size_t)entry*BS2 + r, sum);
+			if(SCALE) {
+				const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
+				const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+			}
+			for(int k = meta.y; k < meta.z; k++) {
+				const int2 pr = __ldg(pairs + k);
+				const double *lb = ilu + (size_t)pr.x*BS2 + r;
+				double lr[BS], u[BS2];
+#pragma unroll
+				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
+				load_block<BS,true>(ilu + (size_t)pr.y*BS2, u);
+#pragma unroll
+				for(int c = 0; c < BS; c++)
+#pragma unroll
+					for(int m = 0; m < BS; m++)
+						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
+			}
+			double *op = ilu + (size_t)entry*BS2 + r;
+			if(changed) {
+				bool ch = false;
+#pragma unroll
+				for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != sum[c]);
+				if(ch) *changed = 1;
+			}
+#pragma unroll
+			for(int c = 0; c < BS; c++) op[c*BS] = sum[c];
+		}
+		// a diagonal entry refreshes the compact inverse: every lane of the group gathers the whole
+		// new block (row m lives in lane m) and solves for its own row of the inverse
+		if(__any_sync(0xffffffffu, isdiag)) {
+			double d[BS2], e[BS], x[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++)
+#pragma unroll
+				for(int m = 0; m < BS; m++)
+					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], g*BS + m);
+			if(isdiag) {
+#pragma unroll
+				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
+				solve_right<BS>(d, e, x);
+				double *ip = dinv + (size_t)meta.w*BS2 + r;
+#pragma unroll
+				for(int c = 0; c < BS; c++) ip[c*BS] = x[c];
+			}
+		}
+		meta = metan;
+		t = tn;
+	}
+}
+
+/// dst block at positions[i] <- src block i
+template <int BS>
+__global__ void scatter_blocks_kernel(const int nbrows, const double *__restrict__ src,
+                                      const int *__restrict__ positions, double *__restrict__ dst)
+{
+	constexpr int BS2 = BS*BS;
+	const long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(e >= (long long)nbrows*BS2) return;
+	const long long i = e / BS2;
+	const int w = (int)(e - i*BS2);
+	dst[(size_t)positions[i]*BS2 + w] = src[e];
+}
+
+void launch_scatter_blocks(const Mat& A, const double *src, const int *positions, double *dst,
+                           cudaStream_t st)
+{
+	const long long n = (long long)A.nbrows*A.bs*A.bs;
+	if(n == 0) return;
+	ProfScope ps(KC_DIAG_INVERT, st);
+	const int grid = div_up(n, 256);
+	switch(A.bs) {
+	case 4: scatter_blocks_kernel<4><<<grid,256,0,st>>>(A.nbrows, src, positions, dst); break;
+	case 5: scatter_blocks_kernel<5><<<grid,256,0,st>>>(A.nbrows, src, positions, dst); break;
+	default: throw Error("scatter blocks: unsupported block size");
+	}
+	B200_LAUNCHED();
+}
+
+/// Persistent grid size: resident CTAs of `kernel` over all SMs (cached per kernel)
+template <typename K>
+static int persistent_grid(K kernel, long long nitems_per_cta_min, long long nitems)
+{
+	static int cached = 0;
+	if(!cached) {
+		int dev = 0, sms = 148, per = 4;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 256, 0) != cudaSuccess || per < 1)
+			per = 4;
+		cached = sms*per;
+	}
+	const long long need = (nitems + nitems_per_cta_min - 1)/nitems_per_cta_min;
+	return (int)std::max<long long>(1, std::min<long long>(cached, need));
+}
+
+template <int BS>
+static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+                               double *dinv, int *changed, cudaStream_t st)
+{
+	constexpr int GPW = 32/BS;
+	const long long per_cta = 8*GPW;
+	if(pl.nlower > 0) {
+		ProfScope ps(KC_FACTOR_LOWER, st);
+		if(scale) {
+			auto k = block_ilu0_lower_kernel<BS,true>;
+			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
+				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
+		} else {
+			auto k = block_ilu0_lower_kernel<BS,false>;
+			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
+				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
+		}
+		B200_LAUNCHED();
+	}
+	if(pl.nupper > 0) {
+		ProfScope ps(KC_FACTOR_UPPER, st);
+		if(scale) {
+			auto k = block_ilu0_upper_kernel<BS,true>;
+			k<<<persistent_grid(k, per_cta, pl.nupper), 256, 0, st>>>(pl.nupper, pl.umeta, A.browind,
+				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
+		} else {
+			auto k = block_ilu0_upper_kernel<BS,false>;
+			k<<<persistent_grid(k, per_cta, pl.nupper), 256, 0, st>>>(pl.nupper, pl.umeta, A.browind,
+				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
+		}
+		B200_LAUNCHED();
+	}
+}
+
 template <int BS, int PHASE, int MODE>
 static void launch_block(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
                          double *resout, int *changed, cudaStream_t st)
@@ -389,6 +645,7 @@ static void launch_any(const Mat& A, const IluPattern *pl, const double *scale, 
 void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st)
 {
 	if(fact_init == B200_INIT_F_NONE) return;
+	ProfScope ps(KC_FACTOR_INIT, st);
 	if(A.bs > 1 && fact_init == B200_INIT_F_ZERO) {
 		// the block version really zeroes (async_blockilu_factor.cpp:65-69); the scalar one falls
 		// through into INIT_F_ORIGINAL (async_ilu_factor.cpp:48-54) - both replicated
@@ -402,10 +659,13 @@ void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *
 }
 
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
-                       int *d_changed, cudaStream_t st)
+                       double *dinv, int *d_changed, cudaStream_t st)
 {
-	launch_any<PH_LOWER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st);
-	launch_any<PH_UPPER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st);
+	if(A.nnzb == 0) return;
+	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, ilu, dinv, d_changed, st); return; }
+	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, ilu, dinv, d_changed, st); return; }
+	{ ProfScope ps(KC_FACTOR_LOWER, st); launch_any<PH_LOWER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
+	{ ProfScope ps(KC_FACTOR_UPPER, st); launch_any<PH_UPPER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
 }
 
 double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,
@@ -462,6 +722,7 @@ void launch_invert_diag_blocks(const Mat& A, const double *src_vals, const int *
                                double *dst, bool dst_is_compact, cudaStream_t st)
 {
 	if(A.nbrows == 0) return;
+	ProfScope ps(KC_DIAG_INVERT, st);
 	if(A.bs == 1) {
 		// only used for the Jacobi-type objects (scalar_jacobi_setup, solverops_jacobi.cpp:141-147)
 		invert_scalars_kernel<<<div_up(A.nbrows,256),256,0,st>>>(A.nbrows, src_vals, positions, dst);

@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256)
 ilu_positions_kernel(const long long nnzb, const int *__restrict__ browptr,
                      const int *__restrict__ bcolind, const int *__restrict__ diagind,
                      const int *__restrict__ browind, const int *__restrict__ posptr,
-                     int *__restrict__ counts, int *__restrict__ lowerp, int *__restrict__ upperp)
+                     int *__restrict__ counts, int *__restrict__ lowerp, int *__restrict__ upperp,
+                     int2 *__restrict__ pairs)
 {
 	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if(j >= nnzb) return;
@@ -57,7 +58,10 @@ ilu_positions_kernel(const long long nnzb, const int *__restrict__ browptr,
 		if(kc >= lim) break;
 		const int ipos = search_sorted(bcolind, __ldg(diagind + kc), __ldg(browptr + kc + 1), col);
 		if(ipos >= 0) {
-			if(FILL) { lowerp[base + cnt] = k; upperp[base + cnt] = ipos; }
+			if(FILL) {
+				lowerp[base + cnt] = k; upperp[base + cnt] = ipos;
+				pairs[base + cnt] = make_int2(k, ipos);
+			}
 			cnt++;
 		}
 	}
@@ -77,6 +81,30 @@ sum_counts_kernel(const long long n, const int *__restrict__ counts, unsigned lo
 	if((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
 }
 
+__global__ void lower_count_kernel(const int n, const int *__restrict__ browptr,
+                                   const int *__restrict__ diagind, int *__restrict__ nl_row)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) nl_row[i] = diagind[i] - browptr[i];
+	else if(i == n) nl_row[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+work_lists_kernel(const long long nnzb, const int *__restrict__ browptr,
+                  const int *__restrict__ bcolind, const int *__restrict__ diagind,
+                  const int *__restrict__ browind, const int *__restrict__ posptr,
+                  const int *__restrict__ loff, int2 *__restrict__ lmeta, int4 *__restrict__ umeta)
+{
+	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(j >= nnzb) return;
+	const int row = browind[j], col = bcolind[j];
+	const int rs = browptr[row], dg = diagind[row], lo = loff[row];
+	if(j < dg)
+		lmeta[lo + (j - rs)] = make_int2((int)j, col);
+	else
+		umeta[(rs - lo) + (j - dg)] = make_int4((int)j, posptr[j], posptr[j+1], col == row ? row : -1);
+}
+
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 {
 	const long long nnzb = A.nnzb;
@@ -92,7 +120,7 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	B200_CUDA(cudaMemsetAsync(counts.p + nnzb, 0, sizeof(int), st));
 	const int grid = div_up(nnzb, 256);
 	ilu_positions_kernel<false><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
-	                                                  nullptr, counts, nullptr, nullptr);
+	                                                  nullptr, counts, nullptr, nullptr, nullptr);
 	B200_LAUNCHED();
 
 	// total in 64 bits first
@@ -117,10 +145,37 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.npos = total;
 	pl.lowerp.alloc(std::max<long long>(total, 1));
 	pl.upperp.alloc(std::max<long long>(total, 1));
+	pl.pairs.alloc(std::max<long long>(total, 1));
 	if(total > 0) {
 		ilu_positions_kernel<true><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind,
 		                                                 A.browind, pl.posptr, nullptr, pl.lowerp,
-		                                                 pl.upperp);
+		                                                 pl.upperp, pl.pairs);
+		B200_LAUNCHED();
+	}
+
+	// per-phase work lists: lower entries and upper entries (row-major order kept)
+	{
+		const int n = A.nbrows;
+		DevBuf<int> nl_row, loff;
+		nl_row.alloc((size_t)n + 1);
+		loff.alloc((size_t)n + 1);
+		lower_count_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, A.browptr, A.diagind, nl_row);
+		B200_LAUNCHED();
+		size_t tb2 = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb2, nl_row.p, loff.p, n + 1, st);
+		DevBuf<char> tmp2;
+		tmp2.alloc(tb2);
+		B200_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, tb2, nl_row.p, loff.p, n + 1, st));
+		g_launches.fetch_add(1);
+		int nl = 0;
+		B200_CUDA(cudaMemcpyAsync(&nl, loff.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		pl.nlower = nl;
+		pl.nupper = nnzb - nl;
+		pl.lmeta.alloc(std::max<long long>(pl.nlower, 1));
+		pl.umeta.alloc(std::max<long long>(pl.nupper, 1));
+		work_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
+		                                        pl.posptr, loff, pl.lmeta, pl.umeta);
 		B200_LAUNCHED();
 	}
 	B200_CUDA(cudaStreamSynchronize(st));

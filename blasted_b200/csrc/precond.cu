@@ -90,6 +90,13 @@ void prec_compute(Prec& P, double precinfo[6])
 			scale = P.scale;
 		}
 		launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, st);
+		// compact inverses of the (initial) diagonal blocks, kept current by the upper launches
+		double *dinv = nullptr;
+		if(A.bs > 1) {
+			if(!P.dinv.p) P.dinv.alloc((size_t)A.nbrows*A.bs*A.bs);
+			dinv = P.dinv;
+			launch_invert_diag_blocks(A, P.ilu, A.diagind, dinv, true, st);
+		}
 
 		// Async_Level_ILU0 (scalar) passes `threadedfactor`=true into the compute_info slot
 		// (solverops_levels_ilu0.cpp:129-130): it always gathers PrecInfo.  Replicated.
@@ -100,7 +107,7 @@ void prec_compute(Prec& P, double precinfo[6])
 
 		if(P.threadedfactor) {
 			for(int sw = 0; sw < P.s.nbuildsweeps; sw++)
-				launch_ilu0_sweep(A, P.pl, scale, P.ilu, nullptr, st);
+				launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, nullptr, st);
 			P.factor_sweeps_done = P.s.nbuildsweeps;
 		}
 		else if(P.s.nbuildsweeps > 0) {
@@ -110,7 +117,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			while(changed && sw < maxsw) {
 				B200_CUDA(cudaMemsetAsync(P.flag, 0, sizeof(int), st));
 				for(int rep = 0; rep < 4; rep++, sw++)
-					launch_ilu0_sweep(A, P.pl, scale, P.ilu, P.flag, st);
+					launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, P.flag, st);
 				B200_CUDA(cudaMemcpyAsync(&changed, P.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
 				B200_CUDA(cudaStreamSynchronize(st));
 			}
@@ -126,9 +133,10 @@ void prec_compute(Prec& P, double precinfo[6])
 			precinfo[5] = dd[0]; precinfo[4] = dd[1]; precinfo[3] = dd[2]; precinfo[2] = dd[3];
 		}
 
-		// invert diagonal blocks in place: async_blockilu_factor.cpp:144-146
+		// "invert diagonal blocks in place" (async_blockilu_factor.cpp:144-146): the inverses of the
+		// final U_ii are already in the compact array; copy them over the diagonal blocks
 		if(A.bs > 1)
-			launch_invert_diag_blocks(A, P.ilu, A.diagind, P.ilu, false, st);
+			launch_scatter_blocks(A, dinv, A.diagind, P.ilu, st);
 	}
 	else throw Error("Invalid preconditioner!");
 

@@ -111,6 +111,7 @@ static void dispatch(const Mat& A, double a, const double *x, double b, const do
                      cudaStream_t st)
 {
 	if(A.nbrows == 0) return;
+	ProfScope ps(KC_SPMV, st);
 	switch(A.bs) {
 	case 1: launch_csr<G3>(A, a, x, b, y, z, st); break;
 	case 3: launch_bsr<3,G3>(A, a, x, b, y, z, st); break;

@@ -377,3 +377,24 @@ class GCR(_IterativeSolver):
     def __init__(self, mat, precond, n_restart: int):
         super().__init__(mat, precond)
         self.restart = n_restart
+
+
+# ---- per-kernel-class device timing (b200_profile_*) ----
+KERNEL_CLASSES = ["factor_lower", "factor_upper", "factor_init", "diag_invert", "tri_lower",
+                  "tri_upper", "spmv", "other"]
+
+
+def profile_enable(on: bool = True) -> None:
+    lib.b200_profile_enable(int(on))
+
+
+def profile_reset() -> None:
+    lib.b200_profile_reset()
+
+
+def profile_get():
+    """{class: (total ms, launches)} accumulated since the last reset."""
+    ms = np.zeros(8)
+    cnt = np.zeros(8, dtype=np.int64)
+    check(lib.b200_profile_get(ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}

@@ -88,6 +88,14 @@ int b200_set_device(int device);
 long long b200_kernel_launches(void);
 void b200_reset_kernel_launches(void);
 
+/** Per-kernel-class device timing (CUDA events on the launching stream), off by default.
+ *  Classes: 0 factor lower launch, 1 factor upper launch, 2 factor init, 3 diagonal inversion /
+ *  scatter, 4 triangular/SGS lower (forward) sweep, 5 upper (backward) sweep, 6 SpMV, 7 other.
+ *  Device-side counterpart of the hand timers in src/blasted_petsc.cpp:416-427,499-510. */
+void b200_profile_enable(int on);
+void b200_profile_reset(void);
+int b200_profile_get(double ms[8], long long count[8]);
+
 /* ---- device-resident matrix: SRMatrixStorage + CSRMatrixView/BSRMatrixView
  *      (include/srmatrixdefs.hpp:38-79, include/blockmatrices.hpp:71-160) ---- */
 
