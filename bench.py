@@ -38,30 +38,51 @@ def make_matrix(rank, cells):
     return matgen.block_stencil((cells, cells), 4, SEED + 1000*rank)
 
 
-def algorithmic_bytes(m, npos, nbuild, napply):
-    """Compulsory HBM traffic of one step (int32 = 4 B, fp64 = 8 B)."""
+def reference_bytes(m, npos, nbuild, napply):
+    """Compulsory DRAM traffic of one step of the REFERENCE algorithm (SURVEY.md section 8(d);
+    int32 = 4 B, fp64 = 8 B): every stored entry is recomputed in every sweep."""
     b, N, nnz = m.bs, m.nbrows, m.nnzb
     b2 = b*b
     sweep = nnz*(24*b2 + 8) + 8*npos + 8*N              # read A, read+write factor, pattern
     init = nnz*16*b2                                     # read A, write factor
     dinv = 16*b2*N + 4*N                                 # diagonal block inversion
     apply_pair = (8*b2 + 4)*nnz + 12*N + 48*b*N          # factor + indices once, vectors
-    return {"factor_sweep": sweep, "init": init, "diag_invert": dinv, "apply_pair": apply_pair,
-            "step": init + nbuild*sweep + dinv + napply*apply_pair}
+    return {"step": init + nbuild*sweep + dinv + napply*apply_pair}
 
 
-def kernel_bytes(m, npos, nlower, nupper):
-    """Algorithmic bytes of ONE launch of each kernel class."""
+def kernel_bytes(m, pat):
+    """Algorithmic bytes of ONE launch of each kernel class of THIS implementation.
+
+    pat: nlower, nupper, nuwork (upper entries with products or on the diagonal; the others are
+    U_ij = A_ij, set by the initialisation and not re-touched), npos_l / npos_u (products of lower /
+    upper entries).  Per launch every distinct array element is counted once."""
+    b, N = m.bs, m.nbrows
+    b2 = b*b
+    # lower launch: {entry,col} list 8 B, A block read, factor block written, posptr 8 B,
+    # U_jj^-1 read once per block row, two partner blocks + 8 B pair per product
+    lower = pat["nlower"]*(16*b2 + 16) + 8*b2*N + pat["npos_l"]*(16*b2 + 8)
+    # upper launch: 16 B work-list item, A block read, factor block written per work entry, two
+    # partner blocks + pair per product, refreshed inverse written per block row
+    upper = pat["nuwork"]*(16*b2 + 16) + pat["npos_u"]*(16*b2 + 8) + 8*b2*N
+    # triangular sweeps: blocks + column indices of their half, browptr/diagind, rhs read,
+    # solution gathered and written; the upper sweep also reads U_ii^-1
+    tri_l = pat["nlower"]*(8*b2 + 4) + 8*N + 24*b*N
+    tri_u = (pat["nupper"] - N)*(8*b2 + 4) + 8*N + 24*b*N + 8*b2*N
+    return {"factor_lower": lower, "factor_upper": upper, "tri_lower": tri_l, "tri_upper": tri_u}
+
+
+def algorithmic_bytes(m, pat, nbuild, napply):
+    """Compulsory HBM traffic of one step of THIS implementation."""
     b, N, nnz = m.bs, m.nbrows, m.nnzb
     b2 = b*b
-    # lower launch: A read + factor write per lower entry, U_jj^-1 read once per block column, list
-    lower = nlower*(16*b2 + 8 + 8) + 8*b2*N
-    # upper launch: A read + factor write per upper entry, two partner blocks per product,
-    # refreshed inverse per row, lists
-    upper = nupper*(16*b2 + 16) + npos*(16*b2 + 8) + 8*b2*N
-    nl_apply = nlower*(8*b2 + 4) + 8*N + 24*b*N          # L sweep: lower blocks, r, y gathered+written
-    nu_apply = nupper*(8*b2 + 4) + 8*N + 24*b*N
-    return {"factor_lower": lower, "factor_upper": upper, "tri_lower": nl_apply, "tri_upper": nu_apply}
+    kb = kernel_bytes(m, pat)
+    init = nnz*16*b2                                     # read A, write factor
+    dinv0 = 16*b2*N + 4*N                                # inverses of the initial diagonal blocks
+    sweep = kb["factor_lower"] + kb["factor_upper"]
+    vec = 3*8*b*N                                        # y := 0, z := y (init_jacobi)
+    apply_pair = kb["tri_lower"] + kb["tri_upper"]
+    return {"factor_sweep": sweep, "init": init, "diag_invert": dinv0, "apply_pair": apply_pair,
+            "step": init + dinv0 + nbuild*sweep + vec + napply*apply_pair}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -142,9 +163,8 @@ def run_reference(args):
         return                                   # rank 0 alone runs the CPU arm
     cells = args.cells
     m = make_matrix(0, cells)
-    from oracle import orc
-    npos = len(orc().ilu_positions(m)[1]) if cells <= 256 else 2*(cells*cells) - 2*cells
-    by = algorithmic_bytes(m, npos, NBUILD, NAPPLY)
+    npos = 2*(cells*cells) - 2*cells                      # 5-point stencil: 2 products per diagonal
+    by = reference_bytes(m, npos, NBUILD, NAPPLY)
     sec, kind, cores = cpu_step_time(m, args.steps, min(args.warmup, 1), NBUILD, NAPPLY)
     val = by["step"]/sec/1e9
     line = {"impl": "reference", "metric": "async_ilu0_factor_apply_hbm_gbs", "value": val,
@@ -198,10 +218,16 @@ def run_b200(args):
     prec.compute()                                        # pattern + first factorisation (setup)
     posptr, lowerp, _ = prec.ilu_positions()
     npos = len(lowerp)
-    nlower = int((m.diagind - m.browptr[:-1]).sum())
-    nupper = m.nnzb - nlower
-    by = algorithmic_bytes(m, npos, NBUILD, NAPPLY)
-    kby = kernel_bytes(m, npos, nlower, nupper)
+    rows = np.repeat(np.arange(m.nbrows), np.diff(m.browptr))
+    cnt = np.diff(posptr)
+    islower = m.bcolind < rows
+    isdiag = m.bcolind == rows
+    pat = {"nlower": int(islower.sum()), "nupper": int((~islower).sum()),
+           "nuwork": int(((~islower) & ((cnt > 0) | isdiag)).sum()),
+           "npos_l": int(cnt[islower].sum()), "npos_u": int(cnt[~islower].sum())}
+    by = algorithmic_bytes(m, pat, NBUILD, NAPPLY)
+    kby = kernel_bytes(m, pat)
+    ref_by = reference_bytes(m, npos, NBUILD, NAPPLY)
 
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
     r_dev = torch.randn(m.dim, dtype=torch.float64, device="cuda", generator=gen)
@@ -300,7 +326,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu:
         csteps = 2
         sec, kind, cores = cpu_step_time(m, csteps, 1, NBUILD, NAPPLY)
-        cpu = {"value": by["step"]/sec/1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+        cpu = {"value": ref_by["step"]/sec/1e9, "unit": "GB/s", "cores": cores, "kind": kind,
                "ms_per_step": sec*1e3,
                "sample": f"full C2 step x {csteps} (1 warm-up) on the host cores, same matrix"}
 
@@ -315,7 +341,9 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "algorithmic_bytes_per_step": by["step"], "frac_of_peak_whole_step": value/world/peak}
+            "algorithmic_bytes_per_step": by["step"],
+            "reference_algorithm_bytes_per_step": ref_by["step"],
+            "frac_of_peak_whole_step": value/world/peak}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

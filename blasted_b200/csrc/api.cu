@@ -3,6 +3,7 @@
  * boundary, error translation.  No exception crosses this file's extern "C" functions.
  */
 #include "common.cuh"
+#include "blockops.cuh"
 #include <cstring>
 #include <cmath>
 
@@ -87,16 +88,23 @@ static void upload_values(Mat& A, const double *vals, bool from_host, cudaStream
 	const size_t n = (size_t)A.nnzb*A.bs*A.bs;
 	if(n == 0) return;
 	const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-	if(A.bs > 1 && A.blockstorage == B200_ROWMAJOR) {
-		// the device layout is always column-major: transpose every block on the way in
-		DevBuf<double> tmp;
-		const double *src = vals;
-		if(from_host) {
-			tmp.alloc(n);
-			B200_CUDA(cudaMemcpyAsync(tmp, vals, n*sizeof(double), kind, st));
-			src = tmp;
+	if(A.bs > 1 && (A.blockstorage == B200_ROWMAJOR) != device_rowmajor(A.bs)) {
+		// the device layout is fixed per block size (blockops.cuh): transpose on the way in,
+		// through a fixed staging buffer so that no matrix-sized temporary is needed
+		if(!from_host) {
+			transpose_blocks(A.bs, A.nnzb, vals, A.vals, st);
+		} else {
+			const long long bs2 = (long long)A.bs*A.bs;
+			const long long chunk_blocks = std::max<long long>(1, (32LL << 20)/(bs2*8));   // 32 MiB
+			A.stage.alloc((size_t)std::min<long long>(chunk_blocks, A.nnzb)*bs2*2);
+			double *buf[2] = { A.stage.p, A.stage.p + (size_t)std::min<long long>(chunk_blocks, A.nnzb)*bs2 };
+			int which = 0;
+			for(long long b0 = 0; b0 < A.nnzb; b0 += chunk_blocks, which ^= 1) {
+				const long long nb = std::min<long long>(chunk_blocks, A.nnzb - b0);
+				B200_CUDA(cudaMemcpyAsync(buf[which], vals + b0*bs2, nb*bs2*sizeof(double), kind, st));
+				transpose_blocks(A.bs, nb, buf[which], A.vals.p + b0*bs2, st);
+			}
 		}
-		transpose_blocks(A.bs, A.nnzb, src, A.vals, st);
 		B200_CUDA(cudaStreamSynchronize(st));
 	} else {
 		B200_CUDA(cudaMemcpyAsync(A.vals, vals, n*sizeof(double), kind, st));
@@ -110,7 +118,7 @@ static void download_blocks(const Mat& A, long long nblocks, const double *d_src
 {
 	const size_t n = (size_t)nblocks*A.bs*A.bs;
 	if(n == 0) return;
-	if(A.bs > 1 && A.blockstorage == B200_ROWMAJOR) {
+	if(A.bs > 1 && (A.blockstorage == B200_ROWMAJOR) != device_rowmajor(A.bs)) {
 		DevBuf<double> tmp;
 		tmp.alloc(n);
 		transpose_blocks(A.bs, nblocks, d_src, tmp, st);
@@ -454,7 +462,15 @@ int b200_prec_get_factor(b200_prec *p, double *iluvals)
 		Prec& P = p->p;
 		if(!P.is_ilu || !P.computed) throw Error("no ILU factor available");
 		B200_CUDA(cudaStreamSynchronize(P.stream));
-		download_blocks(*P.A, P.A->nnzb, P.ilu, iluvals, P.stream);
+		const Mat& A = *P.A;
+		if(A.bs == 1) { download_blocks(A, A.nnzb, P.ilu, iluvals, P.stream); return; }
+		// reference layout: diagonal blocks hold their inverses (async_blockilu_factor.cpp:144-146)
+		DevBuf<double> tmp;
+		const size_t n = (size_t)A.nnzb*A.bs*A.bs;
+		tmp.alloc(n);
+		B200_CUDA(cudaMemcpyAsync(tmp, P.ilu, n*sizeof(double), cudaMemcpyDeviceToDevice, P.stream));
+		launch_scatter_blocks(A, P.dinv, A.diagind, tmp, P.stream);
+		download_blocks(A, A.nnzb, tmp, iluvals, P.stream);
 	});
 }
 
@@ -484,15 +500,9 @@ int b200_prec_ilu_residual(b200_prec *p, double *res)
 		if(!P.is_ilu || !P.computed) throw Error("no ILU factor available");
 		const Mat& A = *P.A;
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
-		if(A.bs == 1) { *res = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, P.stream); return; }
-		// the residual needs UN-inverted diagonal blocks (async_blockilu_factor.cpp:257-297 runs
-		// before :144-146): work on a copy with the diagonal blocks inverted back
-		DevBuf<double> tmp;
-		const size_t n = (size_t)A.nnzb*A.bs*A.bs;
-		tmp.alloc(n);
-		B200_CUDA(cudaMemcpyAsync(tmp, P.ilu, n*sizeof(double), cudaMemcpyDeviceToDevice, P.stream));
-		launch_invert_diag_blocks(A, tmp, A.diagind, tmp, false, P.stream);
-		*res = ilu0_residual(A, P.pl, scale, tmp, P.scratch, P.stream);
+		// the residual is defined with UN-inverted diagonal blocks (async_blockilu_factor.cpp:257-297
+		// runs before :144-146), which is how the device keeps the factor
+		*res = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, P.stream);
 	});
 }
 

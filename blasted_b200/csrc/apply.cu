@@ -20,11 +20,12 @@
  * per level on an explicit row list, perform the exact level-scheduled substitutions.
  *
  * Mapping: scalar - LPR lanes per row + shuffle reduction; block - bs lanes per block-row, lane r
- * owns row r of every block (column-major: each block column is one contiguous bs*8-byte read of
- * the group), x_j is a broadcast load, the bs outputs are one contiguous store.
+ * owns row r of every block (blockops.cuh; bs=4: one 256-bit load per block row), x_j is a
+ * broadcast load, the bs outputs are one contiguous store.
  * HBM-bound: one L+U pair streams the factor once: (8 b^2 + 4) nnzb + 12 N + 48 b N bytes.
  */
 #include "common.cuh"
+#include "blockops.cuh"
 
 namespace b200 {
 
@@ -85,8 +86,8 @@ tri_scalar_kernel(const TriDev a)
 	}
 }
 
-template <int BS, int KIND>
-__global__ void __launch_bounds__(256)
+template <int BS, int KIND, bool VEC>
+__global__ void __launch_bounds__(256, (BS <= 4 ? 8 : 4))
 tri_block_kernel(const TriDev a)
 {
 	constexpr int GPW = 32/BS;
@@ -110,13 +111,9 @@ tri_block_kernel(const TriDev a)
 		for(int jj = js; jj < je; jj++) {
 			if(KIND == TRI_RELAX && jj == d) continue;
 			const int col = __ldg(a.bcolind + jj);
-			const double *blk = a.vals + (size_t)jj*BS2 + r;
-			const double *xs = a.xsrc + (size_t)col*BS;
 			double av[BS], xv[BS];
-#pragma unroll
-			for(int c = 0; c < BS; c++) av[c] = __ldg(blk + c*BS);
-#pragma unroll
-			for(int c = 0; c < BS; c++) xv[c] = ld_iter(xs + c);
+			BlkIO<BS>::template load_row<false>(a.vals + (size_t)jj*BS2, r, av);
+			load_seg<BS,true,VEC>(a.xsrc + (size_t)col*BS, xv);
 #pragma unroll
 			for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
 		}
@@ -131,15 +128,17 @@ tri_block_kernel(const TriDev a)
 	else {
 		// multiply a bs-vector held one entry per lane by a bs x bs block: t_c via shuffles
 		const double tv = (KIND == TRI_SGS_BWD) ? acc : rhs - acc;
-		const double *dblk = nullptr;
+		double dr[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) dr[c] = 0;
 		if(valid)
-			dblk = (KIND == TRI_ILU_UPPER) ? a.vals + (size_t)d*BS2 + r     // pre-inverted U_ii
-			                               : a.dinv + (size_t)row*BS2 + r;  // D_i^-1 of A
+			// compact inverted diagonal blocks: U_ii^-1 (ILU) or D_i^-1 of A (SGS, relaxation)
+			BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
 		double prod = 0;
 #pragma unroll
 		for(int c = 0; c < BS; c++) {
 			const double tc = __shfl_sync(0xffffffffu, tv, g*BS + c);
-			if(valid) prod = fma(__ldg(dblk + c*BS), tc, prod);
+			prod = fma(dr[c], tc, prod);
 		}
 		out = (KIND == TRI_SGS_BWD) ? rhs - prod : prod;
 	}
@@ -166,11 +165,14 @@ static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cu
 	}
 	else if(A.bs == 4) {
 		const long long nwarps = (nrows + 7)/8;
-		tri_block_kernel<4,KIND><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
+		if(aligned32(d.xsrc))
+			tri_block_kernel<4,KIND,true><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
+		else
+			tri_block_kernel<4,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
 	}
 	else if(A.bs == 5) {
 		const long long nwarps = (nrows + 5)/6;
-		tri_block_kernel<5,KIND><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
+		tri_block_kernel<5,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
 	}
 	else throw Error("triangular sweep: unsupported block size " + std::to_string(A.bs));
 	B200_LAUNCHED();
@@ -209,7 +211,7 @@ jacobi_apply_kernel(const int nbrows, const double *__restrict__ dinv, const dou
 	double s = 0;
 #pragma unroll
 	for(int c = 0; c < BS; c++)
-		s = fma(__ldg(dinv + row*BS*BS + c*BS + r), __ldg(rr + row*BS + c), s);
+		s = fma(__ldg(dinv + row*BS*BS + BlkIO<BS>::at(r, c)), __ldg(rr + row*BS + c), s);
 	z[i] = s;
 }
 

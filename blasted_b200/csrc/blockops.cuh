@@ -1,0 +1,169 @@
+/** \file blockops.cuh
+ * \brief Register-level access to small dense blocks and vector segments.
+ *
+ * Device layout of a block (decided per block size, hidden behind BlkIO):
+ *   bs == 4 : ROW-major, 128-byte aligned.  Lane r of a 4-lane group owns row r and moves it with ONE
+ *             256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256, new on sm_100): a group touches each
+ *             128-byte line with a single instruction, which is what keeps the L1 tag stage (one
+ *             line per cycle per SM) off the critical path of these HBM-bound kernels.
+ *   others  : column-major, dense (bs=5: 200-byte blocks, only 8-byte aligned), 64-bit accesses; a
+ *             group reads one block column (bs*8 contiguous bytes) per instruction.
+ * The caller's layout (Eigen ColMajor / RowMajor) is converted at the boundary (storage.cu).
+ *
+ * Arithmetic is written against logical indices: a row is v[c] = B(r,c); a whole block is handed
+ * out "column-major logical", d[c*BS + m] = B(m,c), whatever the storage order.
+ */
+#ifndef B200_BLOCKOPS_CUH
+#define B200_BLOCKOPS_CUH
+
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ 256-bit global accesses
+
+/// read-only data (matrix values, lists): non-coherent path
+__device__ __forceinline__ void ld256_nc(const double *p, double &a, double &b, double &c, double &d)
+{
+	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+/// data other CTAs may be rewriting during this launch (the chaotic iterate): read at L2
+__device__ __forceinline__ void ld256_cg(const double *p, double &a, double &b, double &c, double &d)
+{
+	asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+	             : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d)
+{
+	asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <bool ITER> __device__ __forceinline__ double ld1(const double *p)
+{
+	return ITER ? __ldcg(p) : __ldg(p);
+}
+
+// ------------------------------------------------------------------ blocks
+
+template <int BS>
+struct BlkIO {
+	static constexpr bool ROWMAJOR = false;
+	/// v[c] = B(r,c)
+	template <bool ITER>
+	static __device__ __forceinline__ void load_row(const double *blk, const int r, double (&v)[BS])
+	{
+#pragma unroll
+		for(int c = 0; c < BS; c++) v[c] = ld1<ITER>(blk + c*BS + r);
+	}
+	static __device__ __forceinline__ void store_row(double *blk, const int r, const double (&v)[BS])
+	{
+#pragma unroll
+		for(int c = 0; c < BS; c++) blk[c*BS + r] = v[c];
+	}
+	/// d[c*BS + m] = B(m,c)
+	template <bool ITER>
+	static __device__ __forceinline__ void load_full(const double *blk, double (&d)[BS*BS])
+	{
+#pragma unroll
+		for(int e = 0; e < BS*BS; e++) d[e] = ld1<ITER>(blk + e);
+	}
+	/// position of B(r,c) inside the stored block
+	static __device__ __forceinline__ int at(const int r, const int c) { return c*BS + r; }
+};
+
+template <>
+struct BlkIO<4> {
+	static constexpr bool ROWMAJOR = true;
+	template <bool ITER>
+	static __device__ __forceinline__ void load_row(const double *blk, const int r, double (&v)[4])
+	{
+		if(ITER) ld256_cg(blk + 4*r, v[0], v[1], v[2], v[3]);
+		else ld256_nc(blk + 4*r, v[0], v[1], v[2], v[3]);
+	}
+	static __device__ __forceinline__ void store_row(double *blk, const int r, const double (&v)[4])
+	{
+		st256(blk + 4*r, v[0], v[1], v[2], v[3]);
+	}
+	template <bool ITER>
+	static __device__ __forceinline__ void load_full(const double *blk, double (&d)[16])
+	{
+#pragma unroll
+		for(int m = 0; m < 4; m++) {
+			double t0, t1, t2, t3;
+			if(ITER) ld256_cg(blk + 4*m, t0, t1, t2, t3);
+			else ld256_nc(blk + 4*m, t0, t1, t2, t3);
+			d[0*4 + m] = t0; d[1*4 + m] = t1; d[2*4 + m] = t2; d[3*4 + m] = t3;
+		}
+	}
+	static __device__ __forceinline__ int at(const int r, const int c) { return r*4 + c; }
+};
+
+/// Whether the device stores blocks of this size row-major
+inline bool device_rowmajor(const int bs) { return bs == 4; }
+
+// ------------------------------------------------------------------ vector segments
+
+/// xv[c] = x[c], c < BS.  VEC: the segment is 32-byte aligned (bs == 4 and an aligned base).
+template <int BS, bool ITER, bool VEC>
+__device__ __forceinline__ void load_seg(const double *x, double (&xv)[BS])
+{
+	if(BS == 4 && VEC) {
+		if(ITER) ld256_cg(x, xv[0], xv[1], xv[2], xv[3]);
+		else ld256_nc(x, xv[0], xv[1], xv[2], xv[3]);
+	} else {
+#pragma unroll
+		for(int c = 0; c < BS; c++) xv[c] = ld1<ITER>(x + c);
+	}
+}
+
+inline bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31) == 0; }
+
+// ------------------------------------------------------------------ dense solve in registers
+
+/// Solves x * D = s for the row vector x, with D handed over as d[c*BS + m] = D(m,c).
+/// Equivalent to M x^T = s^T with M = D^T, M(i,j) = d[i*BS + j]: Gaussian elimination with partial
+/// pivoting, fully unrolled, done redundantly by every lane of a group for its own right-hand side.
+/// Stands in for `sum * U_jj.inverse()` (src/kernels/kernels_ilu0_factorize.hpp:91 of the
+/// reference) and for `.inverse()` itself (row r of D^-1 solves x D = e_r).
+template <int BS>
+__device__ __forceinline__ void solve_right(double (&d)[BS*BS], double (&s)[BS], double (&x)[BS])
+{
+	double pinv[BS];
+#pragma unroll
+	for(int p = 0; p < BS; p++) {
+		// bring the largest |M(q,p)|, q >= p, to row p by successive conditional swaps
+#pragma unroll
+		for(int q = p+1; q < BS; q++) {
+			const bool sw = fabs(d[q*BS+p]) > fabs(d[p*BS+p]);
+#pragma unroll
+			for(int j = p; j < BS; j++) {
+				const double a = d[p*BS+j], b = d[q*BS+j];
+				d[p*BS+j] = sw ? b : a;
+				d[q*BS+j] = sw ? a : b;
+			}
+			const double a = s[p], b = s[q];
+			s[p] = sw ? b : a;
+			s[q] = sw ? a : b;
+		}
+		pinv[p] = 1.0/d[p*BS+p];
+#pragma unroll
+		for(int i = p+1; i < BS; i++) {
+			const double f = d[i*BS+p]*pinv[p];
+#pragma unroll
+			for(int j = p+1; j < BS; j++)
+				d[i*BS+j] = fma(-f, d[p*BS+j], d[i*BS+j]);
+			s[i] = fma(-f, s[p], s[i]);
+		}
+	}
+#pragma unroll
+	for(int i = BS-1; i >= 0; i--) {
+		double t = s[i];
+#pragma unroll
+		for(int j = i+1; j < BS; j++)
+			t = fma(-d[i*BS+j], x[j], t);
+		x[i] = t*pinv[i];
+	}
+}
+
+}  // namespace b200
+#endif

@@ -2,8 +2,9 @@
  * \brief Internal definitions shared by the CUDA translation units of libblasted_b200.so.
  *
  * Device storage (the re-design of include/device_container.hpp, srmatrixdefs.hpp of the reference):
- * CSR/BSR arrays resident in HBM, int32 indices, fp64 values, blocks always COLUMN-major on the
- * device (row-major input is transposed at the boundary), bs=4 blocks therefore 128-byte aligned.
+ * CSR/BSR arrays resident in HBM, int32 indices, fp64 values; the block layout on the device is
+ * fixed per block size (blockops.cuh: bs=4 row-major and 128-byte aligned, others column-major) and
+ * the caller's layout is converted at the boundary.
  */
 #ifndef B200_COMMON_CUH
 #define B200_COMMON_CUH
@@ -113,6 +114,7 @@ struct Mat {
 	double avg_row_len = 0;
 	cudaStream_t stream = 0;
 	mutable DevBuf<double> hx, hy, hz;    ///< staging for the *_host entry points
+	DevBuf<double> stage;                 ///< fixed staging buffer for layout-converting uploads
 
 	int dim() const { return nbrows*bs; }
 };
@@ -139,6 +141,9 @@ struct IluPattern {
 	long long nlower = 0, nupper = 0;
 	DevBuf<int2> lmeta;                  ///< per lower entry: {entry, block-column}
 	DevBuf<int4> umeta;                  ///< per upper entry: {entry, pos begin, pos end, row if diagonal else -1}
+	long long nuwork = 0;
+	DevBuf<int4> uwork;                  ///< the subset of umeta that changes between sweeps (has
+	                                     ///< products or is diagonal); the others are U_ij = A_ij
 	DevBuf<int2> pairs;                  ///< {lowerp[k], upperp[k]} interleaved
 	bool built = false;
 };
@@ -159,8 +164,10 @@ void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st);
 void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st);
 /// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
 /// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
+/// `all_upper`: also recompute the upper entries without products (needed once when the initial
+/// guess did not already set them to the scaled A, i.e. for INIT_F_ZERO / INIT_F_NONE).
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
-                       double *dinv, int *d_changed, cudaStream_t st);
+                       double *dinv, int *d_changed, bool all_upper, cudaStream_t st);
 /// dst[positions[i]] <- src[i] for nbrows blocks (copies the compact inverted diagonal blocks into
 /// the factor, the reference's in-place inversion, async_blockilu_factor.cpp:144-146)
 void launch_scatter_blocks(const Mat& A, const double *src_compact, const int *positions, double *dst,

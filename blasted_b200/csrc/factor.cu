@@ -31,6 +31,7 @@
  * block nnzb (24 b^2 + 8) + 8 npos + 8 N.
  */
 #include "common.cuh"
+#include "blockops.cuh"
 #include <cub/device/device_reduce.cuh>
 
 namespace b200 {
@@ -38,69 +39,6 @@ namespace b200 {
 // Loads of the iterate that other CTAs may be rewriting: go to L2 (ld.global.cg) so that values
 // written earlier in the same launch are observed (L1 is not coherent across SMs).
 __device__ __forceinline__ double ld_iter(const double *p) { return __ldcg(p); }
-
-// ------------------------------------------------------------------ dense helpers (registers)
-
-/// Solves x * D = s for the row vector x, D given column-major in registers (D(i,j) = d[j*BS+i]).
-/// Equivalent to M x^T = s^T with M = D^T, i.e. M(i,j) = d[i*BS+j]: Gaussian elimination with
-/// partial pivoting, fully unrolled.  Stands in for `sum * U_jj.inverse()`
-/// (kernels_ilu0_factorize.hpp:91) and for `.inverse()` itself (row r of D^-1 solves x D = e_r).
-template <int BS>
-__device__ __forceinline__ void solve_right(double (&d)[BS*BS], double (&s)[BS], double (&x)[BS])
-{
-	double pinv[BS];
-#pragma unroll
-	for(int p = 0; p < BS; p++) {
-		// bring the largest |M(q,p)|, q >= p, to row p by successive conditional swaps
-#pragma unroll
-		for(int q = p+1; q < BS; q++) {
-			const bool sw = fabs(d[q*BS+p]) > fabs(d[p*BS+p]);
-#pragma unroll
-			for(int j = p; j < BS; j++) {
-				const double a = d[p*BS+j], b = d[q*BS+j];
-				d[p*BS+j] = sw ? b : a;
-				d[q*BS+j] = sw ? a : b;
-			}
-			const double a = s[p], b = s[q];
-			s[p] = sw ? b : a;
-			s[q] = sw ? a : b;
-		}
-		pinv[p] = 1.0/d[p*BS+p];
-#pragma unroll
-		for(int i = p+1; i < BS; i++) {
-			const double f = d[i*BS+p]*pinv[p];
-#pragma unroll
-			for(int j = p+1; j < BS; j++)
-				d[i*BS+j] = fma(-f, d[p*BS+j], d[i*BS+j]);
-			s[i] = fma(-f, s[p], s[i]);
-		}
-	}
-#pragma unroll
-	for(int i = BS-1; i >= 0; i--) {
-		double t = s[i];
-#pragma unroll
-		for(int j = i+1; j < BS; j++)
-			t = fma(-d[i*BS+j], x[j], t);
-		x[i] = t*pinv[i];
-	}
-}
-
-/// Loads a whole column-major block into registers
-template <int BS, bool ITER>
-__device__ __forceinline__ void load_block(const double *p, double (&d)[BS*BS])
-{
-	if(BS % 2 == 0) {
-		const double2 *p2 = reinterpret_cast<const double2*>(p);
-#pragma unroll
-		for(int e = 0; e < BS*BS/2; e++) {
-			const double2 v = ITER ? __ldcg(p2 + e) : __ldg(p2 + e);
-			d[2*e] = v.x; d[2*e+1] = v.y;
-		}
-	} else {
-#pragma unroll
-		for(int e = 0; e < BS*BS; e++) d[e] = ITER ? __ldcg(p + e) : __ldg(p + e);
-	}
-}
 
 // ------------------------------------------------------------------ scaling vector
 
@@ -256,9 +194,7 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 	}
 	if(active) {
 		double sum[BS];
-		const double *ap = avals + (size_t)entry*BS2 + r;
-#pragma unroll
-		for(int c = 0; c < BS; c++) sum[c] = __ldg(ap + c*BS);
+		BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 		if(SCALE) {
 			// scaleBlock: val(i,j) *= scale[brow*bs+i]*scale[bcol*bs+j]  (kernels_ilu0_factorize.hpp:61-69)
 			const double sr = __ldg(scale + (size_t)row*BS + r);
@@ -269,12 +205,9 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 		if(MODE == MODE_SWEEP || MODE == MODE_RESIDUAL) {
 			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
 			for(int k = ps; k < pe; k++) {
-				const double *lb = ilu + (size_t)__ldg(lowerp + k)*BS2 + r;
-				const double *ub = ilu + (size_t)__ldg(upperp + k)*BS2;
 				double lr[BS], u[BS2];
-#pragma unroll
-				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
-				load_block<BS,true>(ub, u);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)__ldg(lowerp + k)*BS2, r, lr);
+				BlkIO<BS>::template load_full<true>(ilu + (size_t)__ldg(upperp + k)*BS2, u);
 #pragma unroll
 				for(int c = 0; c < BS; c++)
 #pragma unroll
@@ -283,14 +216,13 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 			}
 		}
 
-		double *op = ilu + (size_t)entry*BS2 + r;
+		double *op = ilu + (size_t)entry*BS2;
 		if(MODE == MODE_RESIDUAL) {
 			double cur[BS];
-#pragma unroll
-			for(int c = 0; c < BS; c++) cur[c] = ld_iter(op + c*BS);
+			BlkIO<BS>::template load_row<true>(op, r, cur);
 			if(lower) {
 				double d[BS2];
-				load_block<BS,true>(ilu + (size_t)__ldg(diagind + col)*BS2, d);
+				BlkIO<BS>::template load_full<true>(ilu + (size_t)__ldg(diagind + col)*BS2, d);
 #pragma unroll
 				for(int c = 0; c < BS; c++)
 #pragma unroll
@@ -309,7 +241,7 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 				const size_t dpos = (size_t)__ldg(diagind + col)*BS2;
 				if(MODE == MODE_INIT_SGS) {
 					// D = (scaled) diagonal block of A: async_blockilu_factor.cpp:221-250
-					load_block<BS,false>(avals + dpos, d);
+					BlkIO<BS>::template load_full<false>(avals + dpos, d);
 					if(SCALE) {
 #pragma unroll
 						for(int c = 0; c < BS; c++)
@@ -318,26 +250,11 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 								d[c*BS+m] *= __ldg(scale + (size_t)col*BS + m)*__ldg(scale + (size_t)col*BS + c);
 					}
 				} else
-					load_block<BS,true>(ilu + dpos, d);
+					BlkIO<BS>::template load_full<true>(ilu + dpos, d);
 				solve_right<BS>(d, sum, x);
-				if(changed) {
-					bool ch = false;
-#pragma unroll
-					for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != x[c]);
-					if(ch) *changed = 1;
-				}
-#pragma unroll
-				for(int c = 0; c < BS; c++) op[c*BS] = x[c];
-			} else {
-				if(changed) {
-					bool ch = false;
-#pragma unroll
-					for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != sum[c]);
-					if(ch) *changed = 1;
-				}
-#pragma unroll
-				for(int c = 0; c < BS; c++) op[c*BS] = sum[c];
-			}
+				BlkIO<BS>::store_row(op, r, x);
+			} else
+				BlkIO<BS>::store_row(op, r, sum);
 		}
 	}
 	if(MODE == MODE_RESIDUAL) {
@@ -370,14 +287,18 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 // Upper entry (i,j), i<=j: U_ij = A_ij - sum_k L_ik U_kj; a diagonal entry also refreshes dinv[i].
 
 template <int BS>
-__device__ __forceinline__ void load_row_strided(const double *p, double (&v)[BS])
+__device__ __forceinline__ bool row_differs(const double *blk, const int r, const double (&v)[BS])
 {
+	double cur[BS];
+	BlkIO<BS>::template load_row<true>(blk, r, cur);
+	bool ch = false;
 #pragma unroll
-	for(int c = 0; c < BS; c++) v[c] = __ldg(p + c*BS);
+	for(int c = 0; c < BS; c++) ch |= (cur[c] != v[c]);
+	return ch;
 }
 
 template <int BS, bool SCALE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (BS <= 4 ? 3 : 2))
 block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
                         const int *__restrict__ browind, const double *__restrict__ avals,
                         const int *__restrict__ posptr, const int2 *__restrict__ pairs,
@@ -404,8 +325,8 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 		if(meta.x >= 0) {
 			const int entry = meta.x, col = meta.y;
 			double sum[BS], di[BS2];
-			load_row_strided<BS>(avals + (size_t)entry*BS2 + r, sum);
-			load_block<BS,false>(dinv + (size_t)col*BS2, di);
+			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
+			BlkIO<BS>::template load_full<false>(dinv + (size_t)col*BS2, di);
 			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
 			if(SCALE) {
 				const int row = __ldg(browind + entry);
@@ -415,11 +336,9 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 			}
 			for(int k = ps; k < pe; k++) {
 				const int2 pr = __ldg(pairs + k);
-				const double *lb = ilu + (size_t)pr.x*BS2 + r;
 				double lr[BS], u[BS2];
-#pragma unroll
-				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
-				load_block<BS,true>(ilu + (size_t)pr.y*BS2, u);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_full<true>(ilu + (size_t)pr.y*BS2, u);
 #pragma unroll
 				for(int c = 0; c < BS; c++)
 #pragma unroll
@@ -434,15 +353,9 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 				for(int m = 0; m < BS; m++) a = fma(sum[m], di[c*BS+m], a);
 				out[c] = a;
 			}
-			double *op = ilu + (size_t)entry*BS2 + r;
-			if(changed) {
-				bool ch = false;
-#pragma unroll
-				for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != out[c]);
-				if(ch) *changed = 1;
-			}
-#pragma unroll
-			for(int c = 0; c < BS; c++) op[c*BS] = out[c];              // single final store per value
+			double *op = ilu + (size_t)entry*BS2;
+			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
+			BlkIO<BS>::store_row(op, r, out);                            // single final store
 		}
 		meta = metan;
 		t = tn;
@@ -479,7 +392,7 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 		double sum[BS];
 		if(active) {
 			const int entry = meta.x;
-			load_row_strided<BS>(avals + (size_t)entry*BS2 + r, sum);
+			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 			if(SCALE) {
 				const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
 				const double sr = __ldg(scale + (size_t)row*BS + r);
@@ -488,26 +401,18 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 			}
 			for(int k = meta.y; k < meta.z; k++) {
 				const int2 pr = __ldg(pairs + k);
-				const double *lb = ilu + (size_t)pr.x*BS2 + r;
 				double lr[BS], u[BS2];
-#pragma unroll
-				for(int m = 0; m < BS; m++) lr[m] = ld_iter(lb + m*BS);
-				load_block<BS,true>(ilu + (size_t)pr.y*BS2, u);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_full<true>(ilu + (size_t)pr.y*BS2, u);
 #pragma unroll
 				for(int c = 0; c < BS; c++)
 #pragma unroll
 					for(int m = 0; m < BS; m++)
 						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
 			}
-			double *op = ilu + (size_t)entry*BS2 + r;
-			if(changed) {
-				bool ch = false;
-#pragma unroll
-				for(int c = 0; c < BS; c++) ch |= (ld_iter(op + c*BS) != sum[c]);
-				if(ch) *changed = 1;
-			}
-#pragma unroll
-			for(int c = 0; c < BS; c++) op[c*BS] = sum[c];
+			double *op = ilu + (size_t)entry*BS2;
+			if(changed && row_differs<BS>(op, r, sum)) *changed = 1;
+			BlkIO<BS>::store_row(op, r, sum);
 		}
 		// a diagonal entry refreshes the compact inverse: every lane of the group gathers the whole
 		// new block (row m lives in lane m) and solves for its own row of the inverse
@@ -522,9 +427,7 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 #pragma unroll
 				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
 				solve_right<BS>(d, e, x);
-				double *ip = dinv + (size_t)meta.w*BS2 + r;
-#pragma unroll
-				for(int c = 0; c < BS; c++) ip[c*BS] = x[c];
+				BlkIO<BS>::store_row(dinv + (size_t)meta.w*BS2, r, x);
 			}
 		}
 		meta = metan;
@@ -579,8 +482,10 @@ static int persistent_grid(K kernel, long long nitems_per_cta_min, long long nit
 
 template <int BS>
 static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
-                               double *dinv, int *changed, cudaStream_t st)
+                               double *dinv, int *changed, bool all_upper, cudaStream_t st)
 {
+	const long long nup = all_upper ? pl.nupper : pl.nuwork;
+	const int4 *uplist = all_upper ? pl.umeta.p : pl.uwork.p;
 	constexpr int GPW = 32/BS;
 	const long long per_cta = 8*GPW;
 	if(pl.nlower > 0) {
@@ -596,15 +501,15 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 		}
 		B200_LAUNCHED();
 	}
-	if(pl.nupper > 0) {
+	if(nup > 0) {
 		ProfScope ps(KC_FACTOR_UPPER, st);
 		if(scale) {
 			auto k = block_ilu0_upper_kernel<BS,true>;
-			k<<<persistent_grid(k, per_cta, pl.nupper), 256, 0, st>>>(pl.nupper, pl.umeta, A.browind,
+			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
 				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
 		} else {
 			auto k = block_ilu0_upper_kernel<BS,false>;
-			k<<<persistent_grid(k, per_cta, pl.nupper), 256, 0, st>>>(pl.nupper, pl.umeta, A.browind,
+			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
 				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
 		}
 		B200_LAUNCHED();
@@ -659,11 +564,11 @@ void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *
 }
 
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
-                       double *dinv, int *d_changed, cudaStream_t st)
+                       double *dinv, int *d_changed, bool all_upper, cudaStream_t st)
 {
 	if(A.nnzb == 0) return;
-	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, ilu, dinv, d_changed, st); return; }
-	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, ilu, dinv, d_changed, st); return; }
+	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, ilu, dinv, d_changed, all_upper, st); return; }
+	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, ilu, dinv, d_changed, all_upper, st); return; }
 	{ ProfScope ps(KC_FACTOR_LOWER, st); launch_any<PH_LOWER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
 	{ ProfScope ps(KC_FACTOR_UPPER, st); launch_any<PH_UPPER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
 }
@@ -698,17 +603,14 @@ invert_blocks_kernel(const int nbrows, const double *src, const int *__restrict_
 	size_t spos = 0;
 	if(active) {
 		spos = positions ? (size_t)__ldg(positions + rowl) : (size_t)rowl;
-		load_block<BS,true>(src + spos*BS2, d);
+		BlkIO<BS>::template load_full<true>(src + spos*BS2, d);
 #pragma unroll
 		for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
 		solve_right<BS>(d, e, x);          // row r of the inverse
 	}
 	__syncwarp();                          // all lanes have read the block before anyone overwrites it
-	if(active) {
-		double *op = dst + (dst_compact ? (size_t)rowl : spos)*BS2 + r;
-#pragma unroll
-		for(int c = 0; c < BS; c++) op[c*BS] = x[c];
-	}
+	if(active)
+		BlkIO<BS>::store_row(dst + (dst_compact ? (size_t)rowl : spos)*BS2, r, x);
 }
 
 __global__ void invert_scalars_kernel(const int n, const double *__restrict__ src,
@@ -754,11 +656,11 @@ __global__ void diag_dom_kernel(const int nbrows, const int *__restrict__ browpt
 	const int dp = diagind[row];
 	double l = 0, u = 0;
 	for(int c = 0; c < BS; c++)
-		if(c != r) u += fabs(vals[(size_t)dp*BS2 + c*BS + r]);
+		if(c != r) u += fabs(vals[(size_t)dp*BS2 + BlkIO<BS>::at(r, c)]);
 	for(int jj = dp+1; jj < browptr[row+1]; jj++)
-		for(int c = 0; c < BS; c++) u += fabs(vals[(size_t)jj*BS2 + c*BS + r]);
+		for(int c = 0; c < BS; c++) u += fabs(vals[(size_t)jj*BS2 + BlkIO<BS>::at(r, c)]);
 	for(int jj = browptr[row]; jj < dp; jj++)
-		for(int c = 0; c < BS; c++) l += fabs(vals[(size_t)jj*BS2 + c*BS + r]);
+		for(int c = 0; c < BS; c++) l += fabs(vals[(size_t)jj*BS2 + BlkIO<BS>::at(r, c)]);
 	ddl[i] = 1.0 - l;
 	ddu[i] = 1.0 - u/fabs(vals[(size_t)dp*BS2 + r*BS + r]);
 }

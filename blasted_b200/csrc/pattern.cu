@@ -18,6 +18,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 namespace b200 {
 
@@ -105,6 +106,15 @@ work_lists_kernel(const long long nnzb, const int *__restrict__ browptr,
 		umeta[(rs - lo) + (j - dg)] = make_int4((int)j, posptr[j], posptr[j+1], col == row ? row : -1);
 }
 
+__global__ void upper_work_flags_kernel(const long long n, const int4 *__restrict__ umeta,
+                                        char *__restrict__ flags)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(t >= n) return;
+	const int4 m = umeta[t];
+	flags[t] = (m.z > m.y || m.w >= 0) ? 1 : 0;      // has products, or is a diagonal entry
+}
+
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 {
 	const long long nnzb = A.nnzb;
@@ -177,6 +187,31 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 		work_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
 		                                        pl.posptr, loff, pl.lmeta, pl.umeta);
 		B200_LAUNCHED();
+
+		// upper entries that change from sweep to sweep: those with products, and the diagonal
+		// entries (which refresh the compact inverse).  The rest satisfy U_ij = A_ij identically.
+		pl.nuwork = 0;
+		pl.uwork.alloc(std::max<long long>(pl.nupper, 1));
+		if(pl.nupper > 0) {
+			DevBuf<char> flags;
+			DevBuf<int> d_nsel;
+			flags.alloc(pl.nupper);
+			d_nsel.alloc(1);
+			upper_work_flags_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, pl.umeta, flags);
+			B200_LAUNCHED();
+			size_t tb3 = 0;
+			cub::DeviceSelect::Flagged(nullptr, tb3, pl.umeta.p, flags.p, pl.uwork.p, d_nsel.p,
+			                           (int)pl.nupper, st);
+			DevBuf<char> tmp3;
+			tmp3.alloc(tb3);
+			B200_CUDA(cub::DeviceSelect::Flagged(tmp3.p, tb3, pl.umeta.p, flags.p, pl.uwork.p, d_nsel.p,
+			                                     (int)pl.nupper, st));
+			g_launches.fetch_add(1);
+			int nsel = 0;
+			B200_CUDA(cudaMemcpyAsync(&nsel, d_nsel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+			B200_CUDA(cudaStreamSynchronize(st));
+			pl.nuwork = nsel;
+		}
 	}
 	B200_CUDA(cudaStreamSynchronize(st));
 	pl.built = true;

@@ -105,9 +105,15 @@ void prec_compute(Prec& P, double precinfo[6])
 		if(info && precinfo)
 			precinfo[1] = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
 
+		// INIT_F_ORIGINAL / INIT_F_SGS already leave U_ij = (scaled) A_ij in every upper entry; the
+		// entries without products never change from that, so only the first sweep after another
+		// kind of initial guess has to touch them
+		const bool const_upper_set = (P.s.fact_inittype == B200_INIT_F_ORIGINAL ||
+		                              P.s.fact_inittype == B200_INIT_F_SGS ||
+		                              (A.bs == 1 && P.s.fact_inittype == B200_INIT_F_ZERO));
 		if(P.threadedfactor) {
 			for(int sw = 0; sw < P.s.nbuildsweeps; sw++)
-				launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, nullptr, st);
+				launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, nullptr, sw == 0 && !const_upper_set, st);
 			P.factor_sweeps_done = P.s.nbuildsweeps;
 		}
 		else if(P.s.nbuildsweeps > 0) {
@@ -117,7 +123,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			while(changed && sw < maxsw) {
 				B200_CUDA(cudaMemsetAsync(P.flag, 0, sizeof(int), st));
 				for(int rep = 0; rep < 4; rep++, sw++)
-					launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, P.flag, st);
+					launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, P.flag, sw == 0 && !const_upper_set, st);
 				B200_CUDA(cudaMemcpyAsync(&changed, P.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
 				B200_CUDA(cudaStreamSynchronize(st));
 			}
@@ -134,9 +140,9 @@ void prec_compute(Prec& P, double precinfo[6])
 		}
 
 		// "invert diagonal blocks in place" (async_blockilu_factor.cpp:144-146): the inverses of the
-		// final U_ii are already in the compact array; copy them over the diagonal blocks
-		if(A.bs > 1)
-			launch_scatter_blocks(A, dinv, A.diagind, P.ilu, st);
+		// final U_ii are already in the compact array `dinv`, which is what the device triangular
+		// solves read; the factor keeps U_ii itself and b200_prec_get_factor() substitutes the
+		// inverses when the reference-layout factor is asked for.
 	}
 	else throw Error("Invalid preconditioner!");
 
@@ -218,6 +224,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
 		const bool levelled = P.uses_levels || !P.threadedapply;
 		TriArgs a; a.vals = P.ilu; a.row_begin = 0; a.row_end = A.nbrows;
+		a.dinv = (A.bs > 1) ? P.dinv.p : nullptr;       // compact U_ii^-1 (blocks)
 		if(levelled) {
 			// Async_Level_ILU0::apply (solverops_levels_ilu0.cpp:58-105,148-192), and the exact
 			// triangular solves of the sequential variants

@@ -9,11 +9,12 @@
  *  - CSR: a group of LPR lanes (2..32, chosen from the mean row length) per row; consecutive groups
  *    take consecutive rows, so a warp's loads of vals/bcolind cover one contiguous span; partial
  *    sums are combined with warp shuffles.
- *  - BSR: a group of bs lanes per block-row, lane r owns row r of every block: the group reads
- *    each column of a (column-major) block as one contiguous bs*8-byte segment, the x segment is a
- *    broadcast load, no shuffles are needed and the bs results are written contiguously.
+ *  - BSR: a group of bs lanes per block-row, lane r owns row r of every block (blockops.cuh: for
+ *    bs=4 one 256-bit load per block row, so a group touches each 128-byte line exactly once); the
+ *    x segment is a broadcast load, no shuffles are needed, the bs results are written contiguously.
  */
 #include "common.cuh"
+#include "blockops.cuh"
 
 namespace b200 {
 
@@ -41,7 +42,7 @@ csr_spmv_kernel(const int nrows, const int *__restrict__ rowptr, const int *__re
 	}
 }
 
-template <int BS, bool G3>
+template <int BS, bool G3, bool VEC>
 __global__ void __launch_bounds__(256)
 bsr_spmv_kernel(const int nbrows, const int *__restrict__ browptr, const int *__restrict__ bcolind,
                 const double *__restrict__ vals, const double *__restrict__ x,
@@ -60,13 +61,9 @@ bsr_spmv_kernel(const int nbrows, const int *__restrict__ browptr, const int *__
 #pragma unroll 2
 	for(int jj = s; jj < e; jj++) {
 		const int col = __ldg(bcolind + jj);
-		const double *blk = vals + (size_t)jj*(BS*BS) + r;
-		const double *xs = x + (size_t)col*BS;
 		double av[BS], xv[BS];
-#pragma unroll
-		for(int c = 0; c < BS; c++) av[c] = __ldg(blk + c*BS);
-#pragma unroll
-		for(int c = 0; c < BS; c++) xv[c] = __ldg(xs + c);
+		BlkIO<BS>::template load_row<false>(vals + (size_t)jj*(BS*BS), r, av);
+		load_seg<BS,false,VEC>(x + (size_t)col*BS, xv);
 #pragma unroll
 		for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
 	}
@@ -102,7 +99,10 @@ static void launch_bsr(const Mat& A, double a, const double *x, double b, const 
 	constexpr int GPW = 32/BS;
 	const long long nwarps = ((long long)A.nbrows + GPW - 1)/GPW;
 	const int grid = div_up(nwarps*32, 256);
-	bsr_spmv_kernel<BS,G3><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
+	if(BS == 4 && aligned32(x))
+		bsr_spmv_kernel<BS,G3,true><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
+	else
+		bsr_spmv_kernel<BS,G3,false><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
 	B200_LAUNCHED();
 }
 
