@@ -70,6 +70,7 @@ static void finish_matrix(Mat& A, const int *h_diagind, cudaStream_t st)
 {
 	// row statistics for kernel selection
 	A.avg_row_len = A.nbrows ? (double)A.nnzb/A.nbrows : 0.0;
+	A.max_row_len = max_row_length(A, st);
 	A.browind.alloc(std::max<long long>(A.nnzb, 1));
 	build_browind(A, st);
 	A.diagind.alloc(std::max(A.nbrows, 1));
@@ -463,7 +464,13 @@ int b200_prec_get_factor(b200_prec *p, double *iluvals)
 		if(!P.is_ilu || !P.computed) throw Error("no ILU factor available");
 		B200_CUDA(cudaStreamSynchronize(P.stream));
 		const Mat& A = *P.A;
-		if(A.bs == 1) { download_blocks(A, A.nnzb, P.ilu, iluvals, P.stream); return; }
+		if(A.bs == 1) {
+			DevBuf<double> tmp;
+			tmp.alloc(std::max<long long>(A.nnzb, 1));
+			scalar_ilu0_gather(A, P.pl, P.sf, tmp, P.stream);
+			download_blocks(A, A.nnzb, tmp, iluvals, P.stream);
+			return;
+		}
 		// reference layout: diagonal blocks hold their inverses (async_blockilu_factor.cpp:144-146)
 		DevBuf<double> tmp;
 		const size_t n = (size_t)A.nnzb*A.bs*A.bs;
@@ -502,7 +509,8 @@ int b200_prec_ilu_residual(b200_prec *p, double *res)
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
 		// the residual is defined with UN-inverted diagonal blocks (async_blockilu_factor.cpp:257-297
 		// runs before :144-146), which is how the device keeps the factor
-		*res = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, P.stream);
+		*res = (A.bs == 1) ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, P.stream)
+		                   : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, P.stream);
 	});
 }
 

@@ -32,6 +32,8 @@ namespace b200 {
 __device__ __forceinline__ double ld_iter(const double *p) { return __ldcg(p); }
 
 struct TriDev {
+	const int *part_ptr, *part_col;          ///< scalar split form (else nullptr)
+	const double *part_diag;
 	const int *browptr, *bcolind, *diagind;
 	const double *vals, *dinv, *rhs, *rscale, *xsrc;
 	double *x;
@@ -62,13 +64,21 @@ tri_scalar_kernel(const TriDev a)
 	if(valid) {
 		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
 		row = a.rows ? __ldg(a.rows + idx) : idx;
-		const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
-		d = __ldg(a.diagind + row);
 		int js, je;
-		part_range<KIND>(s, d, e, js, je);
+		const int *cols = a.bcolind;
+		if(a.part_ptr) {
+			// split form: the part is its own CSR array, nothing to skip
+			js = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
+			cols = a.part_col;
+			d = -1;
+		} else {
+			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+			d = __ldg(a.diagind + row);
+			part_range<KIND>(s, d, e, js, je);
+		}
 		for(int j = js + lane; j < je; j += LPR) {
 			if(KIND == TRI_RELAX && j == d) continue;
-			sum = fma(__ldg(a.vals + j), ld_iter(a.xsrc + __ldg(a.bcolind + j)), sum);
+			sum = fma(__ldg(a.vals + j), ld_iter(a.xsrc + __ldg(cols + j)), sum);
 		}
 	}
 #pragma unroll
@@ -79,7 +89,8 @@ tri_scalar_kernel(const TriDev a)
 		if(a.rscale) rhs *= __ldg(a.rscale + row);
 		double out;
 		if(KIND == TRI_ILU_LOWER) out = rhs - sum;
-		else if(KIND == TRI_ILU_UPPER) out = (1.0/__ldg(a.vals + d)) * (rhs - sum);
+		else if(KIND == TRI_ILU_UPPER)
+			out = (1.0/(a.part_ptr ? __ldg(a.part_diag + row) : __ldg(a.vals + d))) * (rhs - sum);
 		else if(KIND == TRI_SGS_FWD || KIND == TRI_RELAX) out = __ldg(a.dinv + row) * (rhs - sum);
 		else out = rhs - __ldg(a.dinv + row)*sum;       // TRI_SGS_BWD
 		a.x[row] = out;
@@ -181,6 +192,7 @@ static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cu
 void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t st)
 {
 	TriDev d;
+	d.part_ptr = a.part_ptr; d.part_col = a.part_col; d.part_diag = a.part_diag;
 	d.browptr = A.browptr; d.bcolind = A.bcolind; d.diagind = A.diagind;
 	d.vals = a.vals; d.dinv = a.dinv; d.rhs = a.rhs; d.rscale = a.rscale;
 	d.xsrc = a.xsrc ? a.xsrc : a.x; d.x = a.x; d.rows = a.rows;

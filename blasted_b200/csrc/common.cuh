@@ -132,6 +132,7 @@ void transpose_blocks(int bs, long long nblocks, const double *in, double *out, 
 void build_browind(const Mat& A, cudaStream_t st);
 /// locate diagonals; returns number of rows without one
 int find_diagonals(Mat& A, cudaStream_t st);
+int max_row_length(const Mat& A, cudaStream_t st);
 
 // pattern.cu
 struct IluPattern {
@@ -145,9 +146,48 @@ struct IluPattern {
 	DevBuf<int4> uwork;                  ///< the subset of umeta that changes between sweeps (has
 	                                     ///< products or is diagonal); the others are U_ij = A_ij
 	DevBuf<int2> pairs;                  ///< {lowerp[k], upperp[k]} interleaved
+	// scalar (bs == 1) split form: strict lower part L, strict upper part U (CSR each) and the
+	// diagonal as separate streams, so that every sweep reads one contiguous array
+	long long nstrict = 0;               ///< strict upper entries (= nupper - nbrows)
+	DevBuf<int> lptr, lcol, uptr, ucol;
+	DevBuf<int4> slmeta;                 ///< per lower entry: {entry, column, pos begin, pos end}
+	DevBuf<int4> suall, suwork;          ///< per upper entry: {entry, pos begin, pos end, dest};
+	                                     ///< dest = index into the U values, or ~row for a diagonal
+	DevBuf<int2> spairs;                 ///< products re-indexed into the split L / U value arrays
 	bool built = false;
 };
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
+
+/// Values of the scalar ILU(0) factor in split form (see IluPattern)
+struct ScalarFactor {
+	DevBuf<double> lval, uval, udiag;
+};
+
+// scalar_ilu.cu
+void scalar_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
+                      ScalarFactor& F, cudaStream_t st);
+void scalar_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
+                       int *d_changed, bool all_upper, cudaStream_t st);
+double scalar_ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale,
+                            const ScalarFactor& F, double *d_scratch, cudaStream_t st);
+/// out[entry] for every stored entry, in the reference's iluvals ordering
+void scalar_ilu0_gather(const Mat& A, const IluPattern& pl, const ScalarFactor& F, double *out,
+                        cudaStream_t st);
+
+// csrstream.cu
+enum StreamKind { STREAM_SPMV, STREAM_GEMV3, STREAM_TRI_LOWER, STREAM_TRI_UPPER };
+struct StreamArgs {
+	const int *ptr = nullptr, *col = nullptr;     ///< CSR part (rows ptr[i]..ptr[i+1])
+	const double *val = nullptr;
+	const double *x = nullptr;                    ///< gathered vector
+	double *out = nullptr;
+	const double *rhs = nullptr, *rscale = nullptr, *diag = nullptr, *yin = nullptr;
+	double alpha = 1, beta = 0;
+	int row_begin = 0, row_end = 0;
+	int descending = 0;
+};
+bool stream_supported(int max_row_len);
+void launch_csr_stream(StreamKind kind, const StreamArgs& a, int max_len, cudaStream_t st);
 
 struct Levels {
 	int mode = B200_LEVELS_DAG;
@@ -191,6 +231,9 @@ struct TriArgs {
 	const int *rows = nullptr;       ///< optional explicit row list (level scheduling)
 	int row_begin = 0, row_end = 0;  ///< range of rows (or of positions in `rows`)
 	bool descending = false;         ///< map CTAs to rows in descending order
+	// scalar split form (bs == 1 ILU): the part to sweep as its own CSR arrays; vals indexes it
+	const int *part_ptr = nullptr, *part_col = nullptr;
+	const double *part_diag = nullptr;
 };
 void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t st);
 void launch_jacobi_apply(const Mat& A, const double *dinv, const double *r, double *z,
@@ -227,6 +270,7 @@ struct Prec {
 	IluPattern pl;
 	Levels levels;
 	DevBuf<double> ilu, scale, ytemp, dinv, xtemp, scratch, dot_partial;
+	ScalarFactor sf;                    ///< bs == 1: the factor lives here (split form), not in `ilu`
 	DevBuf<int> flag;
 	DevBuf<double> hr, hz;              ///< staging for *_host entry points
 	bool computed = false;

@@ -61,7 +61,7 @@ ilu_positions_kernel(const long long nnzb, const int *__restrict__ browptr,
 		if(ipos >= 0) {
 			if(FILL) {
 				lowerp[base + cnt] = k; upperp[base + cnt] = ipos;
-				pairs[base + cnt] = make_int2(k, ipos);
+				if(pairs) pairs[base + cnt] = make_int2(k, ipos);
 			}
 			cnt++;
 		}
@@ -107,12 +107,64 @@ work_lists_kernel(const long long nnzb, const int *__restrict__ browptr,
 }
 
 __global__ void upper_work_flags_kernel(const long long n, const int4 *__restrict__ umeta,
-                                        char *__restrict__ flags)
+                                        char *__restrict__ flags, const bool scalar_form)
 {
 	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if(t >= n) return;
 	const int4 m = umeta[t];
-	flags[t] = (m.z > m.y || m.w >= 0) ? 1 : 0;      // has products, or is a diagonal entry
+	const bool isdiag = scalar_form ? (m.w < 0) : (m.w >= 0);
+	flags[t] = (m.z > m.y || isdiag) ? 1 : 0;         // has products, or is a diagonal entry
+}
+
+// ---- scalar split form (see IluPattern) ----
+
+__global__ void __launch_bounds__(256)
+scalar_lists_kernel(const long long nnz, const int *__restrict__ rowptr,
+                    const int *__restrict__ colind, const int *__restrict__ diagind,
+                    const int *__restrict__ rowind, const int *__restrict__ posptr,
+                    const int *__restrict__ loff, int4 *__restrict__ lmeta, int4 *__restrict__ uall,
+                    int *__restrict__ lcol, int *__restrict__ ucol)
+{
+	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(j >= nnz) return;
+	const int row = rowind[j], col = colind[j];
+	const int rs = rowptr[row], dg = diagind[row], lo = loff[row];
+	const int ps = posptr[j], pe = posptr[j+1];
+	if(j < dg) {
+		const int t = lo + (int)(j - rs);
+		lmeta[t] = make_int4((int)j, col, ps, pe);
+		lcol[t] = col;
+	} else {
+		const int tu = (rs - lo) + (int)(j - dg);          // index among upper entries incl. diagonals
+		if(j == dg) uall[tu] = make_int4((int)j, ps, pe, ~row);
+		else {
+			const int ui = tu - (row + 1);                  // index among strict upper entries
+			uall[tu] = make_int4((int)j, ps, pe, ui);
+			ucol[ui] = col;
+		}
+	}
+}
+
+__global__ void scalar_uptr_kernel(const int n, const int *__restrict__ rowptr,
+                                   const int *__restrict__ loff, int *__restrict__ uptr)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i <= n) uptr[i] = rowptr[i] - loff[i] - i;         // strict upper entries before row i
+}
+
+__global__ void __launch_bounds__(256)
+scalar_pairs_kernel(const long long npos, const int *__restrict__ lowerp,
+                    const int *__restrict__ upperp, const int *__restrict__ rowptr,
+                    const int *__restrict__ diagind, const int *__restrict__ rowind,
+                    const int *__restrict__ loff, int2 *__restrict__ spairs)
+{
+	const long long k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(k >= npos) return;
+	const int p = lowerp[k], q = upperp[k];
+	const int rp = rowind[p], rq = rowind[q];
+	const int li = loff[rp] + (p - rowptr[rp]);
+	const int ui = (rowptr[rq] - loff[rq] - rq) + (q - diagind[rq] - 1);
+	spairs[k] = make_int2(li, ui);
 }
 
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
@@ -155,11 +207,11 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.npos = total;
 	pl.lowerp.alloc(std::max<long long>(total, 1));
 	pl.upperp.alloc(std::max<long long>(total, 1));
-	pl.pairs.alloc(std::max<long long>(total, 1));
+	pl.pairs.alloc(A.bs > 1 ? std::max<long long>(total, 1) : 1);
 	if(total > 0) {
 		ilu_positions_kernel<true><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind,
 		                                                 A.browind, pl.posptr, nullptr, pl.lowerp,
-		                                                 pl.upperp, pl.pairs);
+		                                                 pl.upperp, A.bs > 1 ? pl.pairs.p : nullptr);
 		B200_LAUNCHED();
 	}
 
@@ -182,30 +234,55 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 		B200_CUDA(cudaStreamSynchronize(st));
 		pl.nlower = nl;
 		pl.nupper = nnzb - nl;
-		pl.lmeta.alloc(std::max<long long>(pl.nlower, 1));
-		pl.umeta.alloc(std::max<long long>(pl.nupper, 1));
-		work_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
-		                                        pl.posptr, loff, pl.lmeta, pl.umeta);
-		B200_LAUNCHED();
+		pl.nstrict = pl.nupper - n;
+		DevBuf<int4> *all_list = &pl.umeta, *work_list = &pl.uwork;
+		if(A.bs == 1) {
+			// scalar: split CSR parts + lists indexed into the split value arrays
+			all_list = &pl.suall; work_list = &pl.suwork;
+			pl.slmeta.alloc(std::max<long long>(pl.nlower, 1));
+			pl.suall.alloc(std::max<long long>(pl.nupper, 1));
+			pl.lcol.alloc(std::max<long long>(pl.nlower, 1));
+			pl.ucol.alloc(std::max<long long>(pl.nstrict, 1));
+			pl.lptr.alloc((size_t)n + 1);
+			pl.uptr.alloc((size_t)n + 1);
+			B200_CUDA(cudaMemcpyAsync(pl.lptr, loff, ((size_t)n + 1)*sizeof(int), cudaMemcpyDeviceToDevice, st));
+			scalar_uptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, A.browptr, loff, pl.uptr);
+			B200_LAUNCHED();
+			scalar_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
+			                                          pl.posptr, loff, pl.slmeta, pl.suall, pl.lcol, pl.ucol);
+			B200_LAUNCHED();
+			pl.spairs.alloc(std::max<long long>(total, 1));
+			if(total > 0) {
+				scalar_pairs_kernel<<<div_up(total, 256), 256, 0, st>>>(total, pl.lowerp, pl.upperp,
+					A.browptr, A.diagind, A.browind, loff, pl.spairs);
+				B200_LAUNCHED();
+			}
+		} else {
+			pl.lmeta.alloc(std::max<long long>(pl.nlower, 1));
+			pl.umeta.alloc(std::max<long long>(pl.nupper, 1));
+			work_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
+			                                        pl.posptr, loff, pl.lmeta, pl.umeta);
+			B200_LAUNCHED();
+		}
 
 		// upper entries that change from sweep to sweep: those with products, and the diagonal
 		// entries (which refresh the compact inverse).  The rest satisfy U_ij = A_ij identically.
 		pl.nuwork = 0;
-		pl.uwork.alloc(std::max<long long>(pl.nupper, 1));
+		work_list->alloc(std::max<long long>(pl.nupper, 1));
 		if(pl.nupper > 0) {
 			DevBuf<char> flags;
 			DevBuf<int> d_nsel;
 			flags.alloc(pl.nupper);
 			d_nsel.alloc(1);
-			upper_work_flags_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, pl.umeta, flags);
+			upper_work_flags_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, all_list->p, flags, A.bs == 1);
 			B200_LAUNCHED();
 			size_t tb3 = 0;
-			cub::DeviceSelect::Flagged(nullptr, tb3, pl.umeta.p, flags.p, pl.uwork.p, d_nsel.p,
+			cub::DeviceSelect::Flagged(nullptr, tb3, all_list->p, flags.p, work_list->p, d_nsel.p,
 			                           (int)pl.nupper, st);
 			DevBuf<char> tmp3;
 			tmp3.alloc(tb3);
-			B200_CUDA(cub::DeviceSelect::Flagged(tmp3.p, tb3, pl.umeta.p, flags.p, pl.uwork.p, d_nsel.p,
-			                                     (int)pl.nupper, st));
+			B200_CUDA(cub::DeviceSelect::Flagged(tmp3.p, tb3, all_list->p, flags.p, work_list->p,
+			                                     d_nsel.p, (int)pl.nupper, st));
 			g_launches.fetch_add(1);
 			int nsel = 0;
 			B200_CUDA(cudaMemcpyAsync(&nsel, d_nsel.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -67,9 +67,10 @@ void prec_compute(Prec& P, double precinfo[6])
 		}
 	}
 	else if(P.is_ilu) {
+		const bool scalar = (A.bs == 1);       // scalar factors live in split form (P.sf), see scalar_ilu.cu
 		if(first) {
 			// setup_storage + compute_ILU_positions_CSR_CSR on first call: solverops_ilu0.cpp:190-196,358-363
-			P.ilu.alloc((size_t)A.nnzb*A.bs*A.bs);
+			if(!scalar) P.ilu.alloc((size_t)A.nnzb*A.bs*A.bs);
 			P.ytemp.alloc(A.dim());
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
 			if(P.s.scale) P.scale.alloc(A.dim());
@@ -80,8 +81,9 @@ void prec_compute(Prec& P, double precinfo[6])
 			build_ilu_pattern(A, P.pl, st);
 			// the reference copies A into iluvals at allocation (solverops_ilu0.cpp:160-164,333-337);
 			// this is what INIT_F_NONE then starts from
-			B200_CUDA(cudaMemcpyAsync(P.ilu, A.vals, (size_t)A.nnzb*A.bs*A.bs*sizeof(double),
-			                          cudaMemcpyDeviceToDevice, st));
+			if(scalar) scalar_ilu0_init(A, P.pl, nullptr, B200_INIT_F_ORIGINAL, P.sf, st);
+			else B200_CUDA(cudaMemcpyAsync(P.ilu, A.vals, (size_t)A.nnzb*A.bs*A.bs*sizeof(double),
+			                               cudaMemcpyDeviceToDevice, st));
 			B200_CUDA(cudaEventRecord(P.ev0, st));      // time the factorisation proper
 		}
 		const double *scale = nullptr;
@@ -89,7 +91,8 @@ void prec_compute(Prec& P, double precinfo[6])
 			launch_scaling_vector(A, P.scale, st);
 			scale = P.scale;
 		}
-		launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, st);
+		if(scalar) scalar_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
+		else launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, st);
 		// compact inverses of the (initial) diagonal blocks, kept current by the upper launches
 		double *dinv = nullptr;
 		if(A.bs > 1) {
@@ -103,7 +106,8 @@ void prec_compute(Prec& P, double precinfo[6])
 		const bool info = P.s.compute_precinfo ||
 			(type == B200_ASYNC_LEVEL_ILU0 && A.bs == 1);
 		if(info && precinfo)
-			precinfo[1] = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+			precinfo[1] = scalar ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st)
+			                     : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
 
 		// INIT_F_ORIGINAL / INIT_F_SGS already leave U_ij = (scaled) A_ij in every upper entry; the
 		// entries without products never change from that, so only the first sweep after another
@@ -111,9 +115,13 @@ void prec_compute(Prec& P, double precinfo[6])
 		const bool const_upper_set = (P.s.fact_inittype == B200_INIT_F_ORIGINAL ||
 		                              P.s.fact_inittype == B200_INIT_F_SGS ||
 		                              (A.bs == 1 && P.s.fact_inittype == B200_INIT_F_ZERO));
+		auto sweep = [&](int sw, int *flag) {
+			const bool all_upper = (sw == 0 && !const_upper_set);
+			if(scalar) scalar_ilu0_sweep(A, P.pl, scale, P.sf, flag, all_upper, st);
+			else launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, flag, all_upper, st);
+		};
 		if(P.threadedfactor) {
-			for(int sw = 0; sw < P.s.nbuildsweeps; sw++)
-				launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, nullptr, sw == 0 && !const_upper_set, st);
+			for(int sw = 0; sw < P.s.nbuildsweeps; sw++) sweep(sw, nullptr);
 			P.factor_sweeps_done = P.s.nbuildsweeps;
 		}
 		else if(P.s.nbuildsweeps > 0) {
@@ -122,8 +130,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			const int maxsw = A.nbrows*2 + 16;
 			while(changed && sw < maxsw) {
 				B200_CUDA(cudaMemsetAsync(P.flag, 0, sizeof(int), st));
-				for(int rep = 0; rep < 4; rep++, sw++)
-					launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, P.flag, sw == 0 && !const_upper_set, st);
+				for(int rep = 0; rep < 4; rep++, sw++) sweep(sw, P.flag);
 				B200_CUDA(cudaMemcpyAsync(&changed, P.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
 				B200_CUDA(cudaStreamSynchronize(st));
 			}
@@ -131,9 +138,16 @@ void prec_compute(Prec& P, double precinfo[6])
 		}
 
 		if(info && precinfo) {
-			precinfo[0] = ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+			precinfo[0] = scalar ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st)
+			                     : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
 			double dd[4];
-			diag_dominance(A, P.ilu, dd, P.scratch, st);
+			if(scalar) {
+				DevBuf<double> tmp;
+				tmp.alloc(std::max<long long>(A.nnzb, 1));
+				scalar_ilu0_gather(A, P.pl, P.sf, tmp, st);
+				diag_dominance(A, tmp, dd, P.scratch, st);
+			} else
+				diag_dominance(A, P.ilu, dd, P.scratch, st);
 			// PrecInfo layout: [2] upper min, [3] upper avg, [4] lower min, [5] lower avg
 			// (preconditioner_diagnostics.hpp:20-30; arr = {lavg, lmin, uavg, umin})
 			precinfo[5] = dd[0]; precinfo[4] = dd[1]; precinfo[3] = dd[2]; precinfo[2] = dd[3];
@@ -223,17 +237,26 @@ void prec_apply(Prec& P, const double *r, double *z)
 	else if(P.is_ilu) {
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
 		const bool levelled = P.uses_levels || !P.threadedapply;
+		const bool scalar = (A.bs == 1);
 		TriArgs a; a.vals = P.ilu; a.row_begin = 0; a.row_end = A.nbrows;
 		a.dinv = (A.bs > 1) ? P.dinv.p : nullptr;       // compact U_ii^-1 (blocks)
+		// scalar factors are stored split: L part, strict U part, diagonal
+		TriArgs aL = a, aU = a;
+		if(scalar) {
+			aL.vals = P.sf.lval; aL.part_ptr = P.pl.lptr; aL.part_col = P.pl.lcol;
+			aU.vals = P.sf.uval; aU.part_ptr = P.pl.uptr; aU.part_col = P.pl.ucol;
+			aU.part_diag = P.sf.udiag;
+		}
+		const bool stream = scalar && stream_supported(A.max_row_len);
 		if(levelled) {
 			// Async_Level_ILU0::apply (solverops_levels_ilu0.cpp:58-105,148-192), and the exact
 			// triangular solves of the sequential variants
 			if(!P.uses_levels && P.s.apply_inittype == B200_INIT_A_NONE)
 				throw Error(" scalar_ilu0_apply: Invalid init type!");
-			a.rhs = r; a.rscale = scale; a.x = P.ytemp;
-			level_sweep(P, TRI_ILU_LOWER, a, false);
-			a.rhs = P.ytemp; a.rscale = nullptr; a.x = z;
-			level_sweep(P, TRI_ILU_UPPER, a, true);
+			aL.rhs = r; aL.rscale = scale; aL.x = P.ytemp;
+			level_sweep(P, TRI_ILU_LOWER, aL, false);
+			aU.rhs = P.ytemp; aU.rscale = nullptr; aU.x = z;
+			level_sweep(P, TRI_ILU_UPPER, aU, true);
 		}
 		else {
 			// scalar_ilu0_apply / block_ilu0_apply, solverops_ilu0.cpp:56-148,240-321.
@@ -241,14 +264,34 @@ void prec_apply(Prec& P, const double *r, double *z)
 			const int ai = P.s.apply_inittype;
 			if(ai == B200_INIT_A_NONE) throw Error(" scalar_ilu0_apply: Invalid init type!");
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
-			a.rhs = r; a.rscale = scale; a.x = P.ytemp; a.descending = false;
-			for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_ILU_LOWER, a, st);
+			aL.rhs = r; aL.rscale = scale; aL.x = P.ytemp; aL.descending = false;
+			StreamArgs sa;
+			if(stream) {
+				sa.ptr = P.pl.lptr; sa.col = P.pl.lcol; sa.val = P.sf.lval; sa.x = P.ytemp;
+				sa.out = P.ytemp; sa.rhs = r; sa.rscale = scale; sa.row_end = A.nbrows;
+			}
+			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
+				if(stream) {
+					ProfScope ps(KC_TRI_LOWER, st);
+					launch_csr_stream(STREAM_TRI_LOWER, sa, A.max_row_len, st);
+				} else launch_tri_sweep(A, TRI_ILU_LOWER, aL, st);
+			}
 			if(ai == B200_INIT_A_JACOBI)
 				B200_CUDA(cudaMemcpyAsync(z, P.ytemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 			else
 				B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
-			a.rhs = P.ytemp; a.rscale = nullptr; a.x = z; a.descending = true;
-			for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_ILU_UPPER, a, st);
+			aU.rhs = P.ytemp; aU.rscale = nullptr; aU.x = z; aU.descending = true;
+			if(stream) {
+				sa = StreamArgs();
+				sa.ptr = P.pl.uptr; sa.col = P.pl.ucol; sa.val = P.sf.uval; sa.x = z; sa.out = z;
+				sa.rhs = P.ytemp; sa.diag = P.sf.udiag; sa.row_end = A.nbrows; sa.descending = 1;
+			}
+			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
+				if(stream) {
+					ProfScope ps(KC_TRI_UPPER, st);
+					launch_csr_stream(STREAM_TRI_UPPER, sa, A.max_row_len, st);
+				} else launch_tri_sweep(A, TRI_ILU_UPPER, aU, st);
+			}
 		}
 		if(scale) launch_vec_scale_copy(n, scale, z, z, st);      // z := S z
 	}

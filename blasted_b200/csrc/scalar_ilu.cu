@@ -1,0 +1,218 @@
+/** \file scalar_ilu.cu
+ * \brief Scalar (bs = 1) fine-grained asynchronous ILU(0) factorisation on split storage (K1, K4, K10).
+ *
+ * Replaces async_ilu0_factorize_kernel / executeILU0Factorization
+ * (src/kernels/kernels_ilu0_factorize.hpp:19-53, src/async_ilu_factor.cpp:154-177 of the reference),
+ * the scalar initialisations (async_ilu_factor.cpp:47-58,110-151) and scalar_ilu0_nonlinear_res
+ * (:180-217).
+ *
+ * Device storage of the factor: strict lower entries `lval`, strict upper entries `uval` (both in
+ * row order) and the diagonal `udiag`, with work lists built once by pattern.cu.  One thread per
+ * list item: every load of the lists, of A and of the result is unit-stride across the warp, all
+ * lanes are active, and the only gathers are the partner entries of the products and u_jj - the
+ * latter from the compact diagonal array, i.e. contiguous for neighbouring rows.
+ * A sweep is a lower launch (l_ij = (a_ij - sum l_ik u_kj)/u_jj) followed by an upper launch
+ * (u_ij = a_ij - sum l_ik u_kj); upper entries without products satisfy u_ij = a_ij identically and
+ * are only touched when the initial guess did not already set them.
+ * Chaotic-iteration rules as in the reference: one final store per entry, relaxed reads.
+ *
+ * Algorithmic bytes per sweep: lower 16+8+8 B per lower entry (+8 N for u_jj) + 24 B per product;
+ * upper 16+8+8 B per work entry + 24 B per product.
+ */
+#include "common.cuh"
+
+namespace b200 {
+
+namespace {
+
+enum { SM_SWEEP = 0, SM_RESIDUAL = 1, SM_INIT_ORIG = 2, SM_INIT_SGS = 3 };
+
+__device__ __forceinline__ double ld_iter(const double *p) { return __ldcg(p); }
+
+__device__ __forceinline__ void block_sum_atomic(double v, double *out)
+{
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+	__shared__ double wsum[8];
+	if((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		double t = 0;
+		for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
+		if(t != 0) atomicAdd(out, t);
+	}
+}
+
+template <bool SCALE, int MODE>
+__global__ void __launch_bounds__(256)
+scalar_lower_kernel(const long long n, const int4 *__restrict__ lmeta,
+                    const int *__restrict__ browind, const int *__restrict__ diagind,
+                    const double *__restrict__ avals, const double *__restrict__ scale,
+                    const int2 *__restrict__ spairs, double *lval, const double *uval,
+                    const double *udiag, double *__restrict__ resout, int *__restrict__ changed)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	double res = 0;
+	if(t < n) {
+		const int4 m = __ldg(lmeta + t);                 // {entry, col, ps, pe}
+		double sum = __ldg(avals + m.x);
+		if(SCALE) {
+			sum *= __ldg(scale + __ldg(browind + m.x));
+			sum *= __ldg(scale + m.y);
+		}
+		if(MODE == SM_INIT_ORIG) lval[t] = sum;
+		else if(MODE == SM_INIT_SGS) {
+			// L' = L D^-1 on the (scaled) matrix, async_ilu_factor.cpp:110-133 (the reference
+			// indexes `scale` out of bounds there; the intended a_cc s_c s_c is used)
+			const double dg = __ldg(avals + __ldg(diagind + m.y));
+			const double sc = SCALE ? __ldg(scale + m.y) : 1.0;
+			lval[t] = sum * (SCALE ? 1.0/(dg*sc*sc) : 1.0/dg);
+		}
+		else {
+			for(int k = m.z; k < m.w; k++) {
+				const int2 pr = __ldg(spairs + k);
+				sum = fma(-ld_iter(lval + pr.x), ld_iter(uval + pr.y), sum);
+			}
+			const double ujj = ld_iter(udiag + m.y);
+			if(MODE == SM_RESIDUAL) res = fabs(sum - ld_iter(lval + t)*ujj);
+			else {
+				const double out = sum/ujj;
+				if(changed && ld_iter(lval + t) != out) *changed = 1;
+				lval[t] = out;                            // single final store
+			}
+		}
+	}
+	if(MODE == SM_RESIDUAL) block_sum_atomic(res, resout);
+}
+
+template <bool SCALE, int MODE>
+__global__ void __launch_bounds__(256)
+scalar_upper_kernel(const long long n, const int4 *__restrict__ ulist,
+                    const int *__restrict__ browind, const int *__restrict__ bcolind,
+                    const double *__restrict__ avals, const double *__restrict__ scale,
+                    const int2 *__restrict__ spairs, const double *lval, double *uval,
+                    double *udiag, double *__restrict__ resout, int *__restrict__ changed)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	double res = 0;
+	if(t < n) {
+		const int4 m = __ldg(ulist + t);                 // {entry, ps, pe, dest}
+		double sum = __ldg(avals + m.x);
+		if(SCALE) {
+			sum *= __ldg(scale + __ldg(browind + m.x));
+			sum *= __ldg(scale + __ldg(bcolind + m.x));
+		}
+		double *dst = (m.w < 0) ? udiag + (~m.w) : uval + m.w;
+		if(MODE == SM_INIT_ORIG || MODE == SM_INIT_SGS) *dst = sum;
+		else {
+			for(int k = m.y; k < m.z; k++) {
+				const int2 pr = __ldg(spairs + k);
+				sum = fma(-ld_iter(lval + pr.x), ld_iter(uval + pr.y), sum);
+			}
+			if(MODE == SM_RESIDUAL) res = fabs(sum - ld_iter(dst));
+			else {
+				if(changed && ld_iter(dst) != sum) *changed = 1;
+				*dst = sum;
+			}
+		}
+	}
+	if(MODE == SM_RESIDUAL) block_sum_atomic(res, resout);
+}
+
+__global__ void __launch_bounds__(256)
+scalar_gather_kernel(const long long nlower, const long long nupper, const int4 *__restrict__ lmeta,
+                     const int4 *__restrict__ uall, const double *__restrict__ lval,
+                     const double *__restrict__ uval, const double *__restrict__ udiag,
+                     double *__restrict__ out)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(t < nlower) out[lmeta[t].x] = lval[t];
+	else if(t < nlower + nupper) {
+		const int4 m = uall[t - nlower];
+		out[m.x] = (m.w < 0) ? udiag[~m.w] : uval[m.w];
+	}
+}
+
+template <int MODE>
+void run_lower(const Mat& A, const IluPattern& pl, const double *scale, const ScalarFactor& F,
+               double *res, int *changed, cudaStream_t st)
+{
+	if(pl.nlower == 0) return;
+	const int grid = div_up(pl.nlower, 256);
+	if(scale)
+		scalar_lower_kernel<true,MODE><<<grid,256,0,st>>>(pl.nlower, pl.slmeta, A.browind, A.diagind,
+			A.vals, scale, pl.spairs, F.lval.p, F.uval.p, F.udiag.p, res, changed);
+	else
+		scalar_lower_kernel<false,MODE><<<grid,256,0,st>>>(pl.nlower, pl.slmeta, A.browind, A.diagind,
+			A.vals, scale, pl.spairs, F.lval.p, F.uval.p, F.udiag.p, res, changed);
+	B200_LAUNCHED();
+}
+
+template <int MODE>
+void run_upper(const Mat& A, const IluPattern& pl, const double *scale, const ScalarFactor& F,
+               bool all, double *res, int *changed, cudaStream_t st)
+{
+	const long long n = all ? pl.nupper : pl.nuwork;
+	const int4 *list = all ? pl.suall.p : pl.suwork.p;
+	if(n == 0) return;
+	const int grid = div_up(n, 256);
+	if(scale)
+		scalar_upper_kernel<true,MODE><<<grid,256,0,st>>>(n, list, A.browind, A.bcolind, A.vals, scale,
+			pl.spairs, F.lval.p, F.uval.p, F.udiag.p, res, changed);
+	else
+		scalar_upper_kernel<false,MODE><<<grid,256,0,st>>>(n, list, A.browind, A.bcolind, A.vals, scale,
+			pl.spairs, F.lval.p, F.uval.p, F.udiag.p, res, changed);
+	B200_LAUNCHED();
+}
+
+}  // namespace
+
+void scalar_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
+                      ScalarFactor& F, cudaStream_t st)
+{
+	F.lval.alloc(std::max<long long>(pl.nlower, 1));
+	F.uval.alloc(std::max<long long>(pl.nstrict, 1));
+	F.udiag.alloc(std::max(A.nbrows, 1));
+	if(fact_init == B200_INIT_F_NONE) return;
+	ProfScope ps(KC_FACTOR_INIT, st);
+	// INIT_F_ZERO falls through into INIT_F_ORIGINAL in the scalar reference
+	// (src/async_ilu_factor.cpp:48-54, missing break): replicated
+	if(fact_init == B200_INIT_F_SGS) {
+		run_lower<SM_INIT_SGS>(A, pl, scale, F, nullptr, nullptr, st);
+		run_upper<SM_INIT_SGS>(A, pl, scale, F, true, nullptr, nullptr, st);
+	} else {
+		run_lower<SM_INIT_ORIG>(A, pl, scale, F, nullptr, nullptr, st);
+		run_upper<SM_INIT_ORIG>(A, pl, scale, F, true, nullptr, nullptr, st);
+	}
+}
+
+void scalar_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
+                       int *d_changed, bool all_upper, cudaStream_t st)
+{
+	{ ProfScope ps(KC_FACTOR_LOWER, st); run_lower<SM_SWEEP>(A, pl, scale, F, nullptr, d_changed, st); }
+	{ ProfScope ps(KC_FACTOR_UPPER, st); run_upper<SM_SWEEP>(A, pl, scale, F, all_upper, nullptr, d_changed, st); }
+}
+
+double scalar_ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale,
+                            const ScalarFactor& F, double *d_scratch, cudaStream_t st)
+{
+	B200_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(double), st));
+	run_lower<SM_RESIDUAL>(A, pl, scale, F, d_scratch, nullptr, st);
+	run_upper<SM_RESIDUAL>(A, pl, scale, F, true, d_scratch, nullptr, st);
+	double r = 0;
+	B200_CUDA(cudaMemcpyAsync(&r, d_scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	return r;
+}
+
+void scalar_ilu0_gather(const Mat& A, const IluPattern& pl, const ScalarFactor& F, double *out,
+                        cudaStream_t st)
+{
+	const long long n = pl.nlower + pl.nupper;
+	if(n == 0) return;
+	scalar_gather_kernel<<<div_up(n, 256), 256, 0, st>>>(pl.nlower, pl.nupper, pl.slmeta, pl.suall,
+	                                                     F.lval, F.uval, F.udiag, out);
+	B200_LAUNCHED();
+}
+
+}  // namespace b200

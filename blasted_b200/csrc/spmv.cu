@@ -78,6 +78,14 @@ static void launch_csr(const Mat& A, double a, const double *x, double b, const 
 {
 	const int n = A.nbrows;
 	const double avg = A.avg_row_len;
+	if(stream_supported(A.max_row_len)) {
+		// short rows: staged unit-stride stream (csrstream.cu)
+		StreamArgs sa;
+		sa.ptr = A.browptr; sa.col = A.bcolind; sa.val = A.vals; sa.x = x; sa.out = z; sa.yin = y;
+		sa.alpha = a; sa.beta = b; sa.row_end = n;
+		launch_csr_stream(G3 ? STREAM_GEMV3 : STREAM_SPMV, sa, A.max_row_len, st);
+		return;
+	}
 #define B200_CSR_CASE(L)                                                                           \
 	{                                                                                              \
 		const int grid = div_up((long long)n*L, 256);                                              \

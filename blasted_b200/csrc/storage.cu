@@ -84,4 +84,28 @@ int find_diagonals(Mat& A, cudaStream_t st)
 	return missing;
 }
 
+__global__ void max_row_len_kernel(int nbrows, const int *__restrict__ browptr, int *__restrict__ out)
+{
+	int m = 0;
+	for(int row = blockIdx.x*blockDim.x + threadIdx.x; row < nbrows; row += gridDim.x*blockDim.x)
+		m = max(m, browptr[row+1] - browptr[row]);
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+	if((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+int max_row_length(const Mat& A, cudaStream_t st)
+{
+	if(A.nbrows == 0) return 0;
+	DevBuf<int> d;
+	d.alloc(1);
+	B200_CUDA(cudaMemsetAsync(d, 0, sizeof(int), st));
+	max_row_len_kernel<<<std::min(div_up(A.nbrows, 256), 148*8), 256, 0, st>>>(A.nbrows, A.browptr, d);
+	B200_LAUNCHED();
+	int m = 0;
+	B200_CUDA(cudaMemcpyAsync(&m, d, sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	return m;
+}
+
 }  // namespace b200
