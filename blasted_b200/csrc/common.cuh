@@ -91,7 +91,8 @@ struct DevBuf {
 		if(count == n && p) return;
 		release();
 		if(count == 0) return;
-		B200_CUDA(cudaMalloc((void**)&p, count*sizeof(T)));
+		// 64 bytes of slack: bulk async copies round their spans up to 16 bytes
+		B200_CUDA(cudaMalloc((void**)&p, count*sizeof(T) + 64));
 		n = count;
 	}
 	operator T*() const { return p; }
@@ -149,6 +150,7 @@ struct IluPattern {
 	// scalar (bs == 1) split form: strict lower part L, strict upper part U (CSR each) and the
 	// diagonal as separate streams, so that every sweep reads one contiguous array
 	long long nstrict = 0;               ///< strict upper entries (= nupper - nbrows)
+	int max_lower_len = 0, max_upper_len = 0;   ///< longest strict lower / strict upper row part
 	DevBuf<int> lptr, lcol, uptr, ucol;
 	DevBuf<int4> slmeta;                 ///< per lower entry: {entry, column, pos begin, pos end}
 	DevBuf<int4> suall, suwork;          ///< per upper entry: {entry, pos begin, pos end, dest};

@@ -6,11 +6,13 @@
  * src/kernels/kernels_ilu_apply.hpp:15-42, src/solverops_ilu0.cpp:274-314) for short scalar rows,
  * where a lanes-per-row mapping leaves too few bytes in flight per warp to cover HBM latency.
  *
- * One CTA owns a tile of R consecutive rows (R*max_row_len <= CAP entries).  Phase 1: all 256
- * threads walk the tile's CONTIGUOUS span of (value, column) pairs with unit stride - every load
- * is fully coalesced and independent of the others, so many are in flight per thread - multiply
- * by the gathered vector entry and park the products in shared memory.  Phase 2: LPR = 256/R
- * lanes per row add up that row's products from shared memory and write the single final value.
+ * One CTA owns a tile of R consecutive rows (R*max_row_len <= CAP entries).  The tile's CONTIGUOUS
+ * spans of values and column indices are staged in shared memory by two 1D bulk asynchronous
+ * copies (TMA, cp.async.bulk completing on an mbarrier): up to 48 KiB in flight per CTA without a
+ * single register, so a few resident CTAs per SM cover the HBM latency.  Then one thread per row
+ * (or LPR lanes per long row) reads its row from shared memory, gathers the vector entries - for
+ * consecutive rows of a stencil matrix these gathers are consecutive addresses - and writes the
+ * single final value.
  * Tiles are issued in ascending row order for lower/forward sweeps and descending order for
  * upper/backward sweeps (same propagation argument as apply.cu).
  *
@@ -20,15 +22,54 @@
 
 namespace b200 {
 
-constexpr int STREAM_CAP = 4096;       // products staged per CTA (32 KiB of shared memory)
+constexpr int STREAM_CAP = 3584;       // entries staged per CTA: 28 KiB of values + 14 KiB of indices
 
-template <int KIND, int LPR>
+// ---- 1D bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) + mbarrier, CTA-local ----
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	             :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                         unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int KIND, int LPR, int RPT>
 __global__ void __launch_bounds__(256)
 csr_stream_kernel(const StreamArgs a)
 {
-	constexpr int R = 256/LPR;
-	__shared__ double prod[STREAM_CAP];
+	// R rows per tile: short rows -> several rows per thread (RPT), long rows -> several lanes per
+	// row (LPR); exactly one of LPR, RPT is > 1
+	constexpr int R = 256*RPT/LPR;
+	__shared__ __align__(16) double sval[STREAM_CAP + 2];
+	__shared__ __align__(16) int scol[STREAM_CAP + 4];
 	__shared__ int sptr[R + 1];
+	__shared__ __align__(8) unsigned long long bar;
 
 	const int ntiles = gridDim.x;
 	const int tile = a.descending ? ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
@@ -36,44 +77,70 @@ csr_stream_kernel(const StreamArgs a)
 	const int nr = min(R, a.row_end - r0);
 	const int tid = threadIdx.x;
 
-	if(tid < nr) sptr[tid] = __ldg(a.ptr + r0 + tid);
-	if(tid == 0) sptr[nr] = __ldg(a.ptr + r0 + nr);
-	__syncthreads();
-	const int e0 = sptr[0];
-	const int ne = sptr[nr] - e0;
+	for(int i = tid; i <= nr; i += 256) sptr[i] = __ldg(a.ptr + r0 + i);
+	if(tid == 0) mbar_init(&bar, 1);
 
-	// phase 1: unit-stride walk over the tile's entries
-	const int *__restrict__ col = a.col + e0;
-	const double *__restrict__ val = a.val + e0;
-#pragma unroll 4
-	for(int i = tid; i < ne; i += 256) {
-		const int c = __ldg(col + i);
-		const double v = __ldg(val + i);
-		const double xv = (KIND == STREAM_SPMV || KIND == STREAM_GEMV3) ? __ldg(a.x + c)
-		                                                               : __ldcg(a.x + c);
-		prod[i] = v*xv;
-	}
-	__syncthreads();
-
-	// phase 2: LPR lanes per row
-	const int lr = tid / LPR, lane = tid - lr*LPR;
-	double sum = 0;
-	if(lr < nr) {
-		const int s = sptr[lr] - e0, e = sptr[lr + 1] - e0;
-		for(int i = s + lane; i < e; i += LPR) sum += prod[i];
-	}
+	// right-hand sides of this thread's rows: issued now, consumed at the end
+	double rhs[RPT];
+	if(KIND == STREAM_TRI_LOWER || KIND == STREAM_TRI_UPPER || KIND == STREAM_GEMV3) {
 #pragma unroll
-	for(int off = LPR/2; off > 0; off >>= 1)
-		sum += __shfl_down_sync(0xffffffffu, sum, off, LPR);
-	if(lr < nr && lane == 0) {
-		const int row = r0 + lr;
-		if(KIND == STREAM_SPMV) a.out[row] = sum;
-		else if(KIND == STREAM_GEMV3) a.out[row] = a.alpha*sum + a.beta*a.yin[row];
-		else {
-			double rhs = __ldg(a.rhs + row);
-			if(a.rscale) rhs *= __ldg(a.rscale + row);
-			if(KIND == STREAM_TRI_LOWER) a.out[row] = rhs - sum;
-			else a.out[row] = (1.0/__ldg(a.diag + row))*(rhs - sum);     // STREAM_TRI_UPPER
+		for(int k = 0; k < RPT; k++) {
+			const int lr = (LPR > 1) ? tid/LPR : tid + k*256;
+			rhs[k] = 0;
+			if(lr < nr) {
+				const int row = r0 + lr;
+				if(KIND == STREAM_GEMV3) rhs[k] = a.beta*a.yin[row];
+				else {
+					rhs[k] = __ldg(a.rhs + row);
+					if(a.rscale) rhs[k] *= __ldg(a.rscale + row);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	const int e0 = sptr[0], e1 = sptr[nr];
+
+	// stage the tile's contiguous spans of values and column indices with two bulk async copies
+	// (sources rounded down to 16-byte alignment; the arrays are padded at allocation)
+	const int v0 = e0 & ~1, c0 = e0 & ~3;
+	if(e1 > e0) {
+		if(tid == 0) {
+			const unsigned vbytes = (unsigned)(((e1 - v0)*8 + 15) & ~15);
+			const unsigned cbytes = (unsigned)(((e1 - c0)*4 + 15) & ~15);
+			mbar_expect_tx(&bar, vbytes + cbytes);
+			bulk_g2s(sval, a.val + v0, vbytes, &bar);
+			bulk_g2s(scol, a.col + c0, cbytes, &bar);
+		}
+		mbar_wait(&bar, 0);
+	}
+	const double *tv = sval + (e0 - v0) - e0;       // tv[e] = value of entry e
+	const int *tc = scol + (e0 - c0) - e0;
+
+	// rows: gather, multiply, add, single final store per row
+#pragma unroll
+	for(int k = 0; k < RPT; k++) {
+		const int lr = (LPR > 1) ? tid/LPR : tid + k*256;
+		const int lane = (LPR > 1) ? tid - lr*LPR : 0;
+		double sum = 0;
+		if(lr < nr) {
+			const int s = sptr[lr], e = sptr[lr + 1];
+#pragma unroll 4
+			for(int i = s + lane; i < e; i += LPR) {
+				const int c = tc[i];
+				const double xv = (KIND == STREAM_SPMV || KIND == STREAM_GEMV3) ? __ldg(a.x + c)
+				                                                               : __ldcg(a.x + c);
+				sum = fma(tv[i], xv, sum);
+			}
+		}
+#pragma unroll
+		for(int off = LPR/2; off > 0; off >>= 1)
+			sum += __shfl_down_sync(0xffffffffu, sum, off, LPR);
+		if(lr < nr && lane == 0) {
+			const int row = r0 + lr;
+			if(KIND == STREAM_SPMV) a.out[row] = sum;
+			else if(KIND == STREAM_GEMV3) a.out[row] = a.alpha*sum + rhs[k];
+			else if(KIND == STREAM_TRI_LOWER) a.out[row] = rhs[k] - sum;
+			else a.out[row] = (1.0/__ldg(a.diag + row))*(rhs[k] - sum);     // STREAM_TRI_UPPER
 		}
 	}
 }
@@ -83,15 +150,17 @@ static void launch_kind(const StreamArgs& a, int max_len, cudaStream_t st)
 {
 	const int nrows = a.row_end - a.row_begin;
 	if(nrows <= 0) return;
-#define B200_STREAM_CASE(L)                                                        \
+#define B200_STREAM_CASE(L, P)                                                     \
 	{                                                                              \
-		constexpr int R = 256/L;                                                   \
-		csr_stream_kernel<KIND,L><<<div_up(nrows, R), 256, 0, st>>>(a);            \
+		constexpr int R = 256*P/L;                                                 \
+		csr_stream_kernel<KIND,L,P><<<div_up(nrows, R), 256, 0, st>>>(a);          \
 	}
-	if(max_len <= STREAM_CAP/256) B200_STREAM_CASE(1)
-	else if(max_len <= STREAM_CAP/128) B200_STREAM_CASE(2)
-	else if(max_len <= STREAM_CAP/64) B200_STREAM_CASE(4)
-	else B200_STREAM_CASE(8)
+	if(max_len <= STREAM_CAP/1024) B200_STREAM_CASE(1, 4)
+	else if(max_len <= STREAM_CAP/512) B200_STREAM_CASE(1, 2)
+	else if(max_len <= STREAM_CAP/256) B200_STREAM_CASE(1, 1)
+	else if(max_len <= STREAM_CAP/128) B200_STREAM_CASE(2, 1)
+	else if(max_len <= STREAM_CAP/64) B200_STREAM_CASE(4, 1)
+	else B200_STREAM_CASE(8, 1)
 #undef B200_STREAM_CASE
 	B200_LAUNCHED();
 }

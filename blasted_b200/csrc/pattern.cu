@@ -145,6 +145,22 @@ scalar_lists_kernel(const long long nnz, const int *__restrict__ rowptr,
 	}
 }
 
+__global__ void part_max_len_kernel(const int n, const int *__restrict__ rowptr,
+                                    const int *__restrict__ diagind, int *__restrict__ out)
+{
+	int ml = 0, mu = 0;
+	for(int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		ml = max(ml, diagind[i] - rowptr[i]);
+		mu = max(mu, rowptr[i+1] - diagind[i] - 1);
+	}
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) {
+		ml = max(ml, __shfl_down_sync(0xffffffffu, ml, off));
+		mu = max(mu, __shfl_down_sync(0xffffffffu, mu, off));
+	}
+	if((threadIdx.x & 31) == 0) { atomicMax(out, ml); atomicMax(out + 1, mu); }
+}
+
 __global__ void scalar_uptr_kernel(const int n, const int *__restrict__ rowptr,
                                    const int *__restrict__ loff, int *__restrict__ uptr)
 {
@@ -251,6 +267,17 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 			scalar_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
 			                                          pl.posptr, loff, pl.slmeta, pl.suall, pl.lcol, pl.ucol);
 			B200_LAUNCHED();
+			{
+				DevBuf<int> d_ml;
+				d_ml.alloc(2);
+				B200_CUDA(cudaMemsetAsync(d_ml, 0, 2*sizeof(int), st));
+				part_max_len_kernel<<<std::min(div_up(n, 256), 148*8), 256, 0, st>>>(n, A.browptr, A.diagind, d_ml);
+				B200_LAUNCHED();
+				int h[2] = {0, 0};
+				B200_CUDA(cudaMemcpyAsync(h, d_ml, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+				B200_CUDA(cudaStreamSynchronize(st));
+				pl.max_lower_len = h[0]; pl.max_upper_len = h[1];
+			}
 			pl.spairs.alloc(std::max<long long>(total, 1));
 			if(total > 0) {
 				scalar_pairs_kernel<<<div_up(total, 256), 256, 0, st>>>(total, pl.lowerp, pl.upperp,

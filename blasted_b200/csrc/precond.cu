@@ -273,7 +273,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
 				if(stream) {
 					ProfScope ps(KC_TRI_LOWER, st);
-					launch_csr_stream(STREAM_TRI_LOWER, sa, A.max_row_len, st);
+					launch_csr_stream(STREAM_TRI_LOWER, sa, std::max(P.pl.max_lower_len, 1), st);
 				} else launch_tri_sweep(A, TRI_ILU_LOWER, aL, st);
 			}
 			if(ai == B200_INIT_A_JACOBI)
@@ -289,7 +289,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
 				if(stream) {
 					ProfScope ps(KC_TRI_UPPER, st);
-					launch_csr_stream(STREAM_TRI_UPPER, sa, A.max_row_len, st);
+					launch_csr_stream(STREAM_TRI_UPPER, sa, std::max(P.pl.max_upper_len, 1), st);
 				} else launch_tri_sweep(A, TRI_ILU_UPPER, aU, st);
 			}
 		}

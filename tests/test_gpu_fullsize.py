@@ -50,7 +50,7 @@ def test_poisson128_exact_vs_async_solve():
     view = bb.SRMatrixView(m)
     b = view.apply(np.ones(m.dim))
     its = {}
-    for ptype, kw in (("sapilu0", dict(nbuildsweeps=20)), ("ilu0", dict(nbuildsweeps=20, napplysweeps=40))):
+    for ptype, kw in (("sapilu0", dict(nbuildsweeps=20)), ("ilu0", dict(nbuildsweeps=20, napplysweeps=120))):
         p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
             prectype=SOLVER_TYPES[ptype], bs=1, **kw))
         p.compute()

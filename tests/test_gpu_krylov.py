@@ -46,17 +46,19 @@ def test_iteration_counts_match_sequential_reference(key, prec, solver):
     assert res < 5e-10
 
 
-@pytest.mark.parametrize("key,nb,na", [("2dcyl1_bsr4", 30, 60), ("2dcyl1_csr", 30, 60),
-                                       ("msc00726_csr", 60, 300)])
-def test_async_ilu0_iterations_within_5_percent(key, nb, na):
+@pytest.mark.parametrize("key,nb,na,scale", [("2dcyl1_bsr4", 10, 30, False), ("2dcyl1_csr", 30, 60, False),
+                                             ("2dcyl1_bsr4", 10, 30, True), ("msc00726_csr", 30, 60, True)])
+def test_async_ilu0_iterations_within_5_percent(key, nb, na, scale):
     """Async ILU(0) with converged sweeps reproduces the sequential iteration count
     (reference threaded test ThreadedBSR4ILU0Colmajor uses sweeps 10/15, tests/CMakeLists.txt:166-173)."""
     g, gm, m = golden_outputs(), golden_matrices(), case(key)
     b = gm[key.split("_")[0] + "_b"]
     want = int(g[f"its_{key}_seqilu0_bicgstab"][0])
-    # msc00726 has 515 dependency levels and is far from diagonally dominant: massively parallel
-    # (Jacobi-like) triangular sweeps need many more passes than the reference's 4-8 CPU threads
-    x, info = solve(m, "ilu0", "bicgstab", b, nbuildsweeps=nb, napplysweeps=na)
+    # msc00726 is far from diagonally dominant: on ~10^5 concurrent threads the chaotic ILU iteration
+    # is close to a synchronous (Jacobi-type) one, which overflows for this matrix unless the
+    # reference's own symmetric scaling option is switched on (SURVEY.md section 7, measured in
+    # tools/conv_study.py: unscaled needs ~150 sweeps, scaled converges in < 30)
+    x, info = solve(m, "ilu0", "bicgstab", b, nbuildsweeps=nb, napplysweeps=na, scale=scale)
     assert abs(info.iters - want) <= max(1, int(np.ceil(0.05*want))), (info.iters, want)
 
 

@@ -68,5 +68,7 @@ if __name__ == "__main__":
         run("C3-small bsr5 96^3", matgen.block_stencil((96, 96, 96), 5, 2))
     if "p128" in which:
         run("C1 poisson7 128^3", matgen.poisson3d(128))
+    if "p256" in which:
+        run("C1-large poisson7 256^3", matgen.poisson3d(256))
     if "p27" in which:
         run("C4-small poisson27 128^3", matgen.poisson3d(128, 27), scale=True)
