@@ -73,6 +73,15 @@ SYMBOLS = {
     "b200_prec_last_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "b200_solve": (_i, [C.c_char_p, _vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(SolveInfo)]),
     "b200_solve_host": (_i, [C.c_char_p, _vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(SolveInfo)]),
+    "b200_nccl_load": (_i, [C.c_char_p]),
+    "b200_comm_unique_id": (_i, [_vp]),
+    "b200_comm_create": (_i, [_vp, _i, _i, _pp]),
+    "b200_comm_destroy": (None, [_vp]),
+    "b200_comm_allreduce_sum": (_i, [_vp, _vp, _i]),
+    "b200_dist_mat_create": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _pp]),
+    "b200_dist_mat_destroy": (None, [_vp]),
+    "b200_dist_mat_apply": (_i, [_vp, _vp, _vp]),
+    "b200_dist_solve": (_i, [C.c_char_p, _vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(SolveInfo)]),
 }
 
 if not os.path.exists(LIB_PATH):

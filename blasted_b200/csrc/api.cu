@@ -7,8 +7,6 @@
 #include <cstring>
 #include <cmath>
 
-struct b200_mat { b200::Mat m; };
-struct b200_prec { b200::Prec p; };
 
 namespace b200 {
 

@@ -283,6 +283,12 @@ struct Prec {
 	int dim() const { return A->nbrows*A->bs; }
 };
 
+}  // namespace b200
+// the opaque handles of the C ABI
+struct b200_mat { b200::Mat m; };
+struct b200_prec { b200::Prec p; };
+namespace b200 {
+
 void prec_compute(Prec& P, double precinfo[6]);
 void prec_apply(Prec& P, const double *d_r, double *d_z);
 void prec_apply_relax(Prec& P, const double *d_b, double *d_x, int maxits);

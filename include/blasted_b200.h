@@ -199,6 +199,38 @@ int b200_solve_host(const char *solver, const b200_mat *A, b200_prec *M, const d
 int b200_solve(const char *solver, const b200_mat *A, b200_prec *M, const double *d_b, double *d_x,
                double tol, int maxiter, int restart, b200_solve_info *info);
 
+/* ---- one subdomain per GPU: row-partitioned operator, NCCL halo exchange and all-reduce ----
+ * The reference is the LOCAL preconditioner under PETSc's bjacobi/asm (doc/user-doc.md:36-40;
+ * one block per rank, src/blasted_petsc.cpp:604-606); these entry points provide the outer
+ * distributed operator and Krylov reductions that PETSc's MatMult/VecDot provide there. */
+
+typedef struct b200_comm b200_comm;
+typedef struct b200_dist_mat b200_dist_mat;
+
+/** Load NCCL from `path` (NULL: the libnccl.so.2 already in the process / on the loader path). */
+int b200_nccl_load(const char *path);
+/** Rank 0 creates the 128-byte NCCL unique id; the caller broadcasts it to the other ranks. */
+int b200_comm_unique_id(char id[128]);
+int b200_comm_create(const char id[128], int rank, int world, b200_comm **out);
+void b200_comm_destroy(b200_comm *c);
+int b200_comm_allreduce_sum(b200_comm *c, double *vals, int n);
+
+/** diag: the square local diagonal block (local column numbering, what Mat_SeqAIJ of PCBJACOBI
+ *  gives, src/blasted_petsc.cpp:278-298).  offd: the local rows' couplings to other subdomains,
+ *  its column indices pointing into the halo buffer (may be NULL).  The halo buffer is the
+ *  concatenation, in neighbour order, of recv_counts[k] (block) entries from neigh_ranks[k];
+ *  send_idx lists, grouped by neighbour, the local (block) rows sent to it. */
+int b200_dist_mat_create(b200_comm *comm, b200_mat *diag, b200_mat *offd, int nhalo, int nneigh,
+                         const int *neigh_ranks, const int *send_counts, const int *send_idx,
+                         const int *recv_counts, b200_dist_mat **out);
+void b200_dist_mat_destroy(b200_dist_mat *d);
+/** y_local = (A x)_local with halo exchange (device pointers, collective over the communicator). */
+int b200_dist_mat_apply(b200_dist_mat *d, const double *d_x, double *d_y);
+/** The Krylov drivers of b200_solve on the partitioned operator; M is the local (block-Jacobi)
+ *  preconditioner of `diag`.  Collective.  info->iters etc. are identical on every rank. */
+int b200_dist_solve(const char *solver, b200_dist_mat *A, b200_prec *M, const double *d_b,
+                    double *d_x, double tol, int maxiter, int restart, b200_solve_info *info);
+
 #ifdef __cplusplus
 }
 #endif
