@@ -258,9 +258,10 @@ class RefPrec:
 
     def __init__(self, lib, m, prectype, scale=False, nbuildsweeps=1, napplysweeps=1,
                  fact_init="init_original", apply_init="init_jacobi", thread_chunk_size=128,
-                 compute_precinfo=False):
+                 compute_precinfo=False, through_b200_factory=False):
         self.lib, self.m = lib, m
-        self.h = lib.ref_prec_create(prectype.encode(), m.bs, int(m.rowmajor), int(scale),
+        create = lib.ref_prec_create_b200 if through_b200_factory else lib.ref_prec_create
+        self.h = create(prectype.encode(), m.bs, int(m.rowmajor), int(scale),
                                      nbuildsweeps, napplysweeps, INIT_F[fact_init],
                                      INIT_A[apply_init], thread_chunk_size, int(compute_precinfo),
                                      m.nbrows, m.browptr, m.bcolind, m.vals, m.diagind)
@@ -323,6 +324,8 @@ class _Ref:
         L.ref_last_error.restype = C.c_char_p
         L.ref_prec_create.restype = vp
         L.ref_prec_create.argtypes = [C.c_char_p] + [C.c_int] * 10 + [_ip, _ip, _dp, _ip]
+        L.ref_prec_create_b200.restype = vp
+        L.ref_prec_create_b200.argtypes = L.ref_prec_create.argtypes
         L.ref_prec_compute.argtypes = [vp, _dp]
         L.ref_prec_apply.argtypes = [vp, _dp, _dp]
         L.ref_prec_apply_relax.argtypes = [vp, _dp, _dp, C.c_int]
@@ -355,6 +358,11 @@ class _Ref:
 
     def prec(self, m, prectype, **kw) -> RefPrec:
         return RefPrec(self.lib, m, prectype, **kw)
+
+    def prec_b200(self, m, prectype, **kw) -> RefPrec:
+        """The product's device preconditioner created through its C++ B200Factory adapter
+        (blasted_b200/host), i.e. behind the reference's own SRPreconditioner interface."""
+        return RefPrec(self.lib, m, prectype, through_b200_factory=True, **kw)
 
     def spmv(self, m, x):
         y = np.empty(m.dim)

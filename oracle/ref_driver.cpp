@@ -30,6 +30,7 @@
 #include "async_ilu_factor.hpp"
 #include "async_blockilu_factor.hpp"
 #include "../tests/solvers.hpp"
+#include "../blasted_b200/host/b200_solverops.hpp"
 
 using namespace blasted;
 
@@ -111,6 +112,40 @@ void *ref_prec_create(const char *prectype, int bs, int rowmajor, int scale,
 		RefPrec *h = new RefPrec;
 		h->bs = bs;
 		h->p = fact.create_preconditioner(wrap(nbrows, browptr, bcolind, vals, diagind, bs), s);
+		return h;
+	} catch(std::exception& e) {
+		g_err = e.what();
+		return nullptr;
+	}
+}
+
+/// Same as ref_prec_create but through the product's B200Factory (blasted_b200/host): the returned
+/// object is a device preconditioner behind the reference's SRPreconditioner interface, usable by
+/// every other entry point of this driver (compute/apply/solve with the reference's own Krylov code).
+void *ref_prec_create_b200(const char *prectype, int bs, int rowmajor, int scale,
+                           int nbuildsweeps, int napplysweeps, int fact_init, int apply_init,
+                           int thread_chunk_size, int compute_precinfo,
+                           int nbrows, const int *browptr, const int *bcolind, const double *vals,
+                           const int *diagind)
+{
+	try {
+		blasted_b200::B200Factory fact;
+		AsyncSolverSettings s;
+		s.prectype = fact.solverTypeFromString(prectype);
+		s.bs = bs;
+		s.blockstorage = rowmajor ? RowMajor : ColMajor;
+		s.relax = false;
+		s.thread_chunk_size = thread_chunk_size;
+		s.scale = scale;
+		s.nbuildsweeps = nbuildsweeps;
+		s.napplysweeps = napplysweeps;
+		s.fact_inittype = static_cast<FactInit>(fact_init);
+		s.apply_inittype = static_cast<ApplyInit>(apply_init);
+		s.compute_precinfo = compute_precinfo;
+		RefPrec *h = new RefPrec;
+		h->bs = bs;
+		const FactoryBase<double,int>& f = fact;      // through the abstract factory seam
+		h->p = f.create_preconditioner(wrap(nbrows, browptr, bcolind, vals, diagind, bs), s);
 		return h;
 	} catch(std::exception& e) {
 		g_err = e.what();
