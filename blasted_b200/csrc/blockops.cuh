@@ -125,44 +125,65 @@ inline bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31)
 /// pivoting, fully unrolled, done redundantly by every lane of a group for its own right-hand side.
 /// Stands in for `sum * U_jj.inverse()` (src/kernels/kernels_ilu0_factorize.hpp:91 of the
 /// reference) and for `.inverse()` itself (row r of D^-1 solves x D = e_r).
-template <int BS>
-__device__ __forceinline__ void solve_right(double (&d)[BS*BS], double (&s)[BS], double (&x)[BS])
-{
-	double pinv[BS];
+// Elimination step P of solve_right as a template so that every loop bound is a compile-time
+// constant: with runtime-triangular bounds the compiler stops unrolling for BS = 5 and the block
+// falls out of registers into local memory.
+template <int BS, int P>
+struct SolveStep {
+	static __device__ __forceinline__ void eliminate(double (&d)[BS*BS], double (&s)[BS],
+	                                                 double (&pinv)[BS])
+	{
+		// bring the largest |M(q,P)|, q >= P, to row P by successive conditional swaps
 #pragma unroll
-	for(int p = 0; p < BS; p++) {
-		// bring the largest |M(q,p)|, q >= p, to row p by successive conditional swaps
+		for(int q = P+1; q < BS; q++) {
+			const bool sw = fabs(d[q*BS+P]) > fabs(d[P*BS+P]);
 #pragma unroll
-		for(int q = p+1; q < BS; q++) {
-			const bool sw = fabs(d[q*BS+p]) > fabs(d[p*BS+p]);
-#pragma unroll
-			for(int j = p; j < BS; j++) {
-				const double a = d[p*BS+j], b = d[q*BS+j];
-				d[p*BS+j] = sw ? b : a;
+			for(int j = P; j < BS; j++) {
+				const double a = d[P*BS+j], b = d[q*BS+j];
+				d[P*BS+j] = sw ? b : a;
 				d[q*BS+j] = sw ? a : b;
 			}
-			const double a = s[p], b = s[q];
-			s[p] = sw ? b : a;
+			const double a = s[P], b = s[q];
+			s[P] = sw ? b : a;
 			s[q] = sw ? a : b;
 		}
-		pinv[p] = 1.0/d[p*BS+p];
+		pinv[P] = 1.0/d[P*BS+P];
 #pragma unroll
-		for(int i = p+1; i < BS; i++) {
-			const double f = d[i*BS+p]*pinv[p];
+		for(int i = P+1; i < BS; i++) {
+			const double f = d[i*BS+P]*pinv[P];
 #pragma unroll
-			for(int j = p+1; j < BS; j++)
-				d[i*BS+j] = fma(-f, d[p*BS+j], d[i*BS+j]);
-			s[i] = fma(-f, s[p], s[i]);
+			for(int j = P+1; j < BS; j++)
+				d[i*BS+j] = fma(-f, d[P*BS+j], d[i*BS+j]);
+			s[i] = fma(-f, s[P], s[i]);
 		}
+		SolveStep<BS,P+1>::eliminate(d, s, pinv);
 	}
-#pragma unroll
-	for(int i = BS-1; i >= 0; i--) {
+	static __device__ __forceinline__ void substitute(const double (&d)[BS*BS], const double (&s)[BS],
+	                                                  const double (&pinv)[BS], double (&x)[BS])
+	{
+		// rows BS-1-P: back substitution from the bottom
+		constexpr int i = BS - 1 - P;
 		double t = s[i];
 #pragma unroll
 		for(int j = i+1; j < BS; j++)
 			t = fma(-d[i*BS+j], x[j], t);
 		x[i] = t*pinv[i];
+		SolveStep<BS,P+1>::substitute(d, s, pinv, x);
 	}
+};
+template <int BS>
+struct SolveStep<BS,BS> {
+	static __device__ __forceinline__ void eliminate(double (&)[BS*BS], double (&)[BS], double (&)[BS]) {}
+	static __device__ __forceinline__ void substitute(const double (&)[BS*BS], const double (&)[BS],
+	                                                  const double (&)[BS], double (&)[BS]) {}
+};
+
+template <int BS>
+__device__ __forceinline__ void solve_right(double (&d)[BS*BS], double (&s)[BS], double (&x)[BS])
+{
+	double pinv[BS];
+	SolveStep<BS,0>::eliminate(d, s, pinv);
+	SolveStep<BS,0>::substitute(d, s, pinv, x);
 }
 
 }  // namespace b200
