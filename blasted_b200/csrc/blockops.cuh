@@ -69,6 +69,24 @@ struct BlkIO {
 	}
 	/// position of B(r,c) inside the stored block
 	static __device__ __forceinline__ int at(const int r, const int c) { return c*BS + r; }
+	/// Whole block for every lane of the group, WARP-COLLECTIVE (all 32 lanes must call it):
+	/// each lane loads only its own row (blk == nullptr: zeros) and the rows are exchanged with
+	/// shuffles.  25 broadcast loads per lane would cost bs^2 L1 tag look-ups per block; this
+	/// costs bs.  d[c*BS + m] = B(m,c).
+	template <bool ITER>
+	static __device__ __forceinline__ void load_full_group(const double *blk, const int r,
+	                                                       const int gbase, double (&d)[BS*BS])
+	{
+		double row[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) row[c] = 0;
+		if(blk) load_row<ITER>(blk, r, row);
+#pragma unroll
+		for(int c = 0; c < BS; c++)
+#pragma unroll
+			for(int m = 0; m < BS; m++)
+				d[c*BS + m] = __shfl_sync(0xffffffffu, row[c], min(gbase + m, 31));
+	}
 };
 
 template <>
@@ -96,7 +114,53 @@ struct BlkIO<4> {
 		}
 	}
 	static __device__ __forceinline__ int at(const int r, const int c) { return r*4 + c; }
+	/// same interface as the generic version; 4 broadcast 256-bit loads are cheap enough (4 tags)
+	template <bool ITER>
+	static __device__ __forceinline__ void load_full_group(const double *blk, const int, const int,
+	                                                       double (&d)[16])
+	{
+		if(blk) load_full<ITER>(blk, d);
+		else {
+#pragma unroll
+			for(int e = 0; e < 16; e++) d[e] = 0;
+		}
+	}
 };
+
+// ------------------------------------------------------------------ group products via shuffles
+//
+// A group of BS lanes holds a block one row per lane.  Products against a partner block are
+// streamed: the partner's row held by lane m is broadcast entry by entry with warp shuffles, so no
+// lane ever keeps a whole bs x bs partner in registers (register pressure, hence occupancy, is
+// what bounds these latency-sensitive kernels) and no lane issues bs^2 broadcast loads (L1 tag
+// stage).  WARP-COLLECTIVE: all 32 lanes must call these with the same control flow.
+
+/// acc(r,:) -= L(r,:) * U  with  lrow = L(r,:) of this lane and urow = U(r,:) of this lane
+template <int BS>
+__device__ __forceinline__ void group_mul_sub(double (&acc)[BS], const double (&lrow)[BS],
+                                              const double (&urow)[BS], const int gbase)
+{
+#pragma unroll
+	for(int c = 0; c < BS; c++)
+#pragma unroll
+		for(int m = 0; m < BS; m++)
+			acc[c] = fma(-lrow[m], __shfl_sync(0xffffffffu, urow[c], min(gbase + m, 31)), acc[c]);
+}
+
+/// out(r,:) = S(r,:) * D  with  srow = S(r,:) and drow = D(r,:) of this lane
+template <int BS>
+__device__ __forceinline__ void group_mul(double (&out)[BS], const double (&srow)[BS],
+                                          const double (&drow)[BS], const int gbase)
+{
+#pragma unroll
+	for(int c = 0; c < BS; c++) {
+		double a = 0;
+#pragma unroll
+		for(int m = 0; m < BS; m++)
+			a = fma(srow[m], __shfl_sync(0xffffffffu, drow[c], min(gbase + m, 31)), a);
+		out[c] = a;
+	}
+}
 
 /// Whether the device stores blocks of this size row-major
 inline bool device_rowmajor(const int bs) { return bs == 4; }

@@ -298,7 +298,7 @@ __device__ __forceinline__ bool row_differs(const double *blk, const int r, cons
 }
 
 template <int BS, bool SCALE>
-__global__ void __launch_bounds__(256, (BS <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(256, 4)
 block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
                         const int *__restrict__ browind, const double *__restrict__ avals,
                         const int *__restrict__ posptr, const int2 *__restrict__ pairs,
@@ -322,37 +322,42 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 		int2 metan = make_int2(-1, -1);
 		if(lanevalid && tn < nlower) metan = __ldg(lmeta + tn);       // prefetch next item's indices
 
-		if(meta.x >= 0) {
-			const int entry = meta.x, col = meta.y;
-			double sum[BS], di[BS2];
+		// every lane of the warp runs the same instruction stream (the block exchanges below are
+		// warp collectives); lanes without an item work on zeros and store nothing
+		const bool active = meta.x >= 0;
+		const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
+		double sum[BS], drow[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) { sum[c] = 0; drow[c] = 0; }
+		int ps = 0, pe = 0;
+		if(active) {
 			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
-			BlkIO<BS>::template load_full<false>(dinv + (size_t)col*BS2, di);
-			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
-			if(SCALE) {
-				const int row = __ldg(browind + entry);
-				const double sr = __ldg(scale + (size_t)row*BS + r);
+			BlkIO<BS>::template load_row<false>(dinv + (size_t)col*BS2, r, drow);   // row r of U_jj^-1
+			ps = __ldg(posptr + entry); pe = __ldg(posptr + entry + 1);
+		}
+		if(SCALE && active) {
+			const int row = __ldg(browind + entry);
+			const double sr = __ldg(scale + (size_t)row*BS + r);
 #pragma unroll
-				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
-			}
-			for(int k = ps; k < pe; k++) {
-				const int2 pr = __ldg(pairs + k);
-				double lr[BS], u[BS2];
+			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+		}
+		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
+		for(int k = 0; k < nk; k++) {
+			const bool has = ps + k < pe;
+			int2 pr = make_int2(0, 0);
+			if(has) pr = __ldg(pairs + ps + k);
+			double lr[BS], ur[BS];
+#pragma unroll
+			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
+			if(has) {
 				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_full<true>(ilu + (size_t)pr.y*BS2, u);
-#pragma unroll
-				for(int c = 0; c < BS; c++)
-#pragma unroll
-					for(int m = 0; m < BS; m++)
-						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
 			}
-			double out[BS];
-#pragma unroll
-			for(int c = 0; c < BS; c++) {
-				double a = 0;
-#pragma unroll
-				for(int m = 0; m < BS; m++) a = fma(sum[m], di[c*BS+m], a);
-				out[c] = a;
-			}
+			group_mul_sub<BS>(sum, lr, ur, g*BS);
+		}
+		double out[BS];
+		group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
+		if(active) {
 			double *op = ilu + (size_t)entry*BS2;
 			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
 			BlkIO<BS>::store_row(op, r, out);                            // single final store
@@ -362,8 +367,8 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 	}
 }
 
-template <int BS, bool SCALE>
-__global__ void __launch_bounds__(256)
+template <int BS, bool SCALE, bool FUSE_INV>
+__global__ void __launch_bounds__(256, (FUSE_INV ? 3 : 4))
 block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
                         const int *__restrict__ browind, const int *__restrict__ bcolind,
                         const double *__restrict__ avals, const int2 *__restrict__ pairs,
@@ -389,9 +394,11 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 
 		const bool active = meta.x >= 0;
 		const bool isdiag = active && meta.w >= 0;
+		const int entry = active ? meta.x : 0;
 		double sum[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] = 0;
 		if(active) {
-			const int entry = meta.x;
 			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 			if(SCALE) {
 				const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
@@ -399,30 +406,37 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 #pragma unroll
 				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
 			}
-			for(int k = meta.y; k < meta.z; k++) {
-				const int2 pr = __ldg(pairs + k);
-				double lr[BS], u[BS2];
+		}
+		// products: warp-uniform trip count, partner blocks exchanged within the group
+		const int ps = active ? meta.y : 0, pe = active ? meta.z : 0;
+		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
+		for(int k = 0; k < nk; k++) {
+			const bool has = ps + k < pe;
+			int2 pr = make_int2(0, 0);
+			if(has) pr = __ldg(pairs + ps + k);
+			double lr[BS], ur[BS];
+#pragma unroll
+			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
+			if(has) {
 				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_full<true>(ilu + (size_t)pr.y*BS2, u);
-#pragma unroll
-				for(int c = 0; c < BS; c++)
-#pragma unroll
-					for(int m = 0; m < BS; m++)
-						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
 			}
+			group_mul_sub<BS>(sum, lr, ur, g*BS);
+		}
+		if(active) {
 			double *op = ilu + (size_t)entry*BS2;
 			if(changed && row_differs<BS>(op, r, sum)) *changed = 1;
 			BlkIO<BS>::store_row(op, r, sum);
 		}
 		// a diagonal entry refreshes the compact inverse: every lane of the group gathers the whole
 		// new block (row m lives in lane m) and solves for its own row of the inverse
-		if(__any_sync(0xffffffffu, isdiag)) {
+		if(FUSE_INV && __any_sync(0xffffffffu, isdiag)) {
 			double d[BS2], e[BS], x[BS];
 #pragma unroll
 			for(int c = 0; c < BS; c++)
 #pragma unroll
 				for(int m = 0; m < BS; m++)
-					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], g*BS + m);
+					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], min(g*BS + m, 31));
 			if(isdiag) {
 #pragma unroll
 				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
@@ -462,6 +476,10 @@ void launch_scatter_blocks(const Mat& A, const double *src, const int *positions
 	}
 	B200_LAUNCHED();
 }
+
+template <int BS>
+__global__ void invert_blocks_kernel(const int nbrows, const double *src, const int *__restrict__ positions,
+                                     double *dst, const bool dst_compact);
 
 /// Persistent grid size: resident CTAs of `kernel` over all SMs (cached per kernel)
 template <typename K>
@@ -503,16 +521,27 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 	}
 	if(nup > 0) {
 		ProfScope ps(KC_FACTOR_UPPER, st);
+		// bs = 4: the diagonal entries refresh U_ii^-1 inside this launch; bs = 5: the 5x5 pivoted
+		// elimination would cost the launch ~25 registers per thread (occupancy), so the inverses
+		// are refreshed by a separate pass over the N diagonal blocks
+		constexpr bool FUSE = (BS <= 4);
 		if(scale) {
-			auto k = block_ilu0_upper_kernel<BS,true>;
+			auto k = block_ilu0_upper_kernel<BS,true,FUSE>;
 			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
 				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
 		} else {
-			auto k = block_ilu0_upper_kernel<BS,false>;
+			auto k = block_ilu0_upper_kernel<BS,false,FUSE>;
 			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
 				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
 		}
 		B200_LAUNCHED();
+		if(!FUSE) {
+			constexpr int GPWI = 32/BS;
+			const long long nwarps = ((long long)A.nbrows + GPWI - 1)/GPWI;
+			invert_blocks_kernel<BS><<<div_up(nwarps*32, 256), 256, 0, st>>>(A.nbrows, ilu, A.diagind,
+			                                                             dinv, true);
+			B200_LAUNCHED();
+		}
 	}
 }
 
