@@ -88,25 +88,37 @@ def algorithmic_bytes(m, pat, nbuild, napply):
 # ----------------------------------------------------------------------------- clocks
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region: one long-running
+    `nvidia-smi -lms 20` whose lines are collected until stop()."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
@@ -244,6 +256,7 @@ def run_b200(args):
     barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)                                   # let the sampler come up
     sf.profile_reset()
     sf.profile_enable(True)
     bb.reset_kernel_launches()
@@ -258,7 +271,7 @@ def run_b200(args):
     launches = bb.kernel_launches()
     prof = sf.profile_get()
     sf.profile_enable(False)
-    sampler.stop_flag = True
+    sampler.stop()
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -361,8 +374,8 @@ def run_b200(args):
 
 
 def run_fgmres(n, rank, world, dist):
-    """Time to solve A x = b (7-point Poisson n^3, x* = 1) to rel. residual 1e-8 with GCR(30)
-    preconditioned by per-subdomain async ILU(0) (5 build sweeps, 10 apply sweep pairs)."""
+    """Time to solve A x = b (7-point Poisson n^3, x* = 1) to rel. residual 1e-8 with FGMRES(30)
+    preconditioned by per-subdomain async ILU(0) (5 build sweeps, 5 apply sweep pairs; measured fastest in tools/solve_study.py)."""
     import torch
     import blasted_b200 as bb
     from blasted_b200 import solverfactory as sf
@@ -371,13 +384,13 @@ def run_fgmres(n, rank, world, dist):
     comm = Comm.from_torch_distributed() if world > 1 else Comm.single()
     part = poisson3d_slab(n, rank, world)
     A = DistMatrix(comm, part)
-    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=5, napplysweeps=10)
+    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=5, napplysweeps=5)
     prec = bb.SRFactory().create_preconditioner(A.diag, s)
     ones = torch.ones(part.diag.dim, dtype=torch.float64, device="cuda")
     b = A.apply(ones)
     x = torch.zeros_like(b)
     prec.compute()                                         # setup (pattern on device) + warm-up
-    info = A.solve("gcr", prec, b, x, tol=1e-8, maxiter=1000, restart=30)
+    info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=2000, restart=30)
     best = None
     for _ in range(2):
         x.zero_()
@@ -387,7 +400,7 @@ def run_fgmres(n, rank, world, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         prec.compute()
-        info = A.solve("gcr", prec, b, x, tol=1e-8, maxiter=1000, restart=30)
+        info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=2000, restart=30)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -396,7 +409,7 @@ def run_fgmres(n, rank, world, dist):
         best = float(t.item()) if best is None else min(best, float(t.item()))
     err = float((x - 1.0).abs().max().item())
     return {"problem": f"7-point Poisson {n}^3, z-slabs over {world} GPU(s), block-Jacobi async ILU(0) "
-                       "(5,10) + GCR(30), rel. tol 1e-8", "scaling": "strong",
+                       "(5,5) + FGMRES(30), rel. tol 1e-8", "scaling": "strong",
             "unknowns": n**3, "iterations": info.iters, "converged": bool(info.converged),
             "time_to_solve_ms": best, "factor_included": True, "max_abs_error": err}
 
@@ -404,7 +417,7 @@ def run_fgmres(n, rank, world, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=1024, help="cells per side (C2 = 1024)")

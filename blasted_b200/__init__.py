@@ -8,6 +8,6 @@ tests/solvers.hpp); the C++ mirror is blasted_b200/host/b200_solverops.hpp.
 """
 from . import matgen                                         # noqa: F401
 from .solverfactory import (SRFactory, AsyncSolverSettings, Preconditioner, SRMatrixView,   # noqa: F401
-                            CSRMatrixView, BSRMatrixView, PrecInfo, SolveInfo, BiCGSTAB, GCR,
+                            CSRMatrixView, BSRMatrixView, PrecInfo, SolveInfo, BiCGSTAB, GCR, FGMRES,
                             RichardsonSolver, device_count, kernel_launches,
                             reset_kernel_launches, SOLVER_TYPES)

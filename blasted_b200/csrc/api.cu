@@ -149,10 +149,11 @@ struct LocalOps : public KrylovOps {
 		if(M) prec_apply(*M, r, z);
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
-	void dots(int nd, const double *const *a, const double *const *b, double *out) override {
+	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
 		launch_multi_dot(n, nd, a, b, partial, dout, stream);
 		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
 		B200_CUDA(cudaStreamSynchronize(stream));
+		return dout.p;
 	}
 };
 

@@ -106,7 +106,15 @@ void launch_multi_dot(long long n, int nd, const double *const *a, const double 
 	case 5: multi_dot_stage1<5><<<grid,256,0,st>>>(n, p, d_partial); break;
 	case 6: multi_dot_stage1<6><<<grid,256,0,st>>>(n, p, d_partial); break;
 	case 7: multi_dot_stage1<7><<<grid,256,0,st>>>(n, p, d_partial); break;
-	default: multi_dot_stage1<8><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 8: multi_dot_stage1<8><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 9: multi_dot_stage1<9><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 10: multi_dot_stage1<10><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 11: multi_dot_stage1<11><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 12: multi_dot_stage1<12><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 13: multi_dot_stage1<13><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 14: multi_dot_stage1<14><<<grid,256,0,st>>>(n, p, d_partial); break;
+	case 15: multi_dot_stage1<15><<<grid,256,0,st>>>(n, p, d_partial); break;
+	default: multi_dot_stage1<16><<<grid,256,0,st>>>(n, p, d_partial); break;
 	}
 	B200_LAUNCHED();
 	multi_dot_stage2<<<1,256,0,st>>>(nd, grid, d_partial, d_out);
@@ -117,23 +125,37 @@ struct AxpyPtrs { const double *v[32]; };
 
 __global__ void __launch_bounds__(256)
 multi_axpy_kernel(const long long n, const int nv, const AxpyPtrs p, const double *__restrict__ coef,
-                  double *y)
+                  double *y, const double sign)
 {
 	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	double s = y[i];
-	for(int l = 0; l < nv; l++) s = fma(__ldg(coef + l), p.v[l][i], s);
+	for(int l = 0; l < nv; l++) s = fma(sign*__ldg(coef + l), p.v[l][i], s);
 	y[i] = s;
 }
 
+__global__ void vec_scal_kernel(const long long n, const double alpha, const double *__restrict__ in,
+                                double *__restrict__ out)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) out[i] = alpha*in[i];
+}
+
+void launch_vec_scal(long long n, double alpha, const double *in, double *out, cudaStream_t st)
+{
+	if(n == 0) return;
+	vec_scal_kernel<<<div_up(n,256),256,0,st>>>(n, alpha, in, out);
+	B200_LAUNCHED();
+}
+
 void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef, double *y,
-                       cudaStream_t st)
+                       cudaStream_t st, double sign)
 {
 	if(n == 0 || nv == 0) return;
 	if(nv > 32) throw Error("multi_axpy: too many vectors");
 	AxpyPtrs p;
 	for(int l = 0; l < 32; l++) p.v[l] = v[l < nv ? l : 0];
-	multi_axpy_kernel<<<div_up(n,256),256,0,st>>>(n, nv, p, d_coef, y);
+	multi_axpy_kernel<<<div_up(n,256),256,0,st>>>(n, nv, p, d_coef, y, sign);
 	B200_LAUNCHED();
 }
 

@@ -249,7 +249,7 @@ void launch_axpby(long long n, double p, double *z, double q, const double *x, c
 void launch_axpbypcz(long long n, double p, double *z, double q, const double *x, double r,
                      const double *y, cudaStream_t st);
 /// out[0..nd) = dots of pairs (a[i], b[i]); result left on the device in d_out
-constexpr int MAX_DOTS = 8;
+constexpr int MAX_DOTS = 16;
 constexpr int DOT_BLOCKS = 592;      // 148 SMs x 4
 /// d_out[i] = a[i] . b[i] for i < nd <= MAX_DOTS, deterministic two-stage reduction;
 /// d_partial must hold MAX_DOTS*DOT_BLOCKS doubles.  Result stays on the device.
@@ -257,7 +257,9 @@ void launch_multi_dot(long long n, int nd, const double *const *a, const double 
                       double *d_partial, double *d_out, cudaStream_t st);
 /// y += sum_l coef[l] * v[l]  for l < nv (coefficients read from device memory), nv <= 32 per call
 void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef,
-                       double *y, cudaStream_t st);
+                       double *y, cudaStream_t st, double sign = 1.0);
+/// out = alpha * in
+void launch_vec_scal(long long n, double alpha, const double *in, double *out, cudaStream_t st);
 
 // ---------------------------------------------------------------- preconditioner object
 
@@ -304,8 +306,9 @@ struct KrylovOps {
 	virtual void spmv(const double *x, double *y) = 0;
 	virtual void gemv3(double a, const double *x, double b, const double *y, double *z) = 0;
 	virtual void prec(const double *r, double *z) = 0;
-	/// out[i] = a[i].b[i], i < nd, summed over all ranks, returned on the host
-	virtual void dots(int nd, const double *const *a, const double *const *b, double *out) = 0;
+	/// out[i] = a[i].b[i], i < nd, summed over all ranks, returned on the host; the return value
+	/// points to the same results in device memory (valid until the next call)
+	virtual const double *dots(int nd, const double *const *a, const double *const *b, double *out) = 0;
 };
 
 void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, double *d_x,

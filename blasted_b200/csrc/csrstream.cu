@@ -59,15 +59,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int KIND, int LPR, int RPT>
+template <int KIND, int LPR, int RPT, int CAP>
 __global__ void __launch_bounds__(256)
 csr_stream_kernel(const StreamArgs a)
 {
 	// R rows per tile: short rows -> several rows per thread (RPT), long rows -> several lanes per
 	// row (LPR); exactly one of LPR, RPT is > 1
 	constexpr int R = 256*RPT/LPR;
-	__shared__ __align__(16) double sval[STREAM_CAP + 2];
-	__shared__ __align__(16) int scol[STREAM_CAP + 4];
+	__shared__ __align__(16) double sval[CAP + 2];
+	__shared__ __align__(16) int scol[CAP + 4];
 	__shared__ int sptr[R + 1];
 	__shared__ __align__(8) unsigned long long bar;
 
@@ -150,17 +150,24 @@ static void launch_kind(const StreamArgs& a, int max_len, cudaStream_t st)
 {
 	const int nrows = a.row_end - a.row_begin;
 	if(nrows <= 0) return;
-#define B200_STREAM_CASE(L, P)                                                     \
+	// tile shapes: rows per CTA R = 256*RPT/LPR with R*max_len <= CAP staged entries.  Small tiles
+	// (more resident CTAs, staging and row phases of different CTAs overlap) for the short row
+	// parts of the triangular sweeps; the largest tiles for full rows.
+	static const bool small = getenv("B200_STREAM_LARGE") == nullptr;
+#define B200_STREAM_CASE(L, P, C)                                                  \
 	{                                                                              \
 		constexpr int R = 256*P/L;                                                 \
-		csr_stream_kernel<KIND,L,P><<<div_up(nrows, R), 256, 0, st>>>(a);          \
+		csr_stream_kernel<KIND,L,P,C><<<div_up(nrows, R), 256, 0, st>>>(a);        \
 	}
-	if(max_len <= STREAM_CAP/1024) B200_STREAM_CASE(1, 4)
-	else if(max_len <= STREAM_CAP/512) B200_STREAM_CASE(1, 2)
-	else if(max_len <= STREAM_CAP/256) B200_STREAM_CASE(1, 1)
-	else if(max_len <= STREAM_CAP/128) B200_STREAM_CASE(2, 1)
-	else if(max_len <= STREAM_CAP/64) B200_STREAM_CASE(4, 1)
-	else B200_STREAM_CASE(8, 1)
+	const bool tri = (KIND == STREAM_TRI_LOWER || KIND == STREAM_TRI_UPPER);
+	if(tri && small && max_len <= 3) B200_STREAM_CASE(1, 2, 1536)
+	else if(tri && small && max_len <= 7) B200_STREAM_CASE(1, 1, 1792)
+	else if(max_len <= STREAM_CAP/1024) B200_STREAM_CASE(1, 4, STREAM_CAP)
+	else if(max_len <= STREAM_CAP/512) B200_STREAM_CASE(1, 2, STREAM_CAP)
+	else if(max_len <= STREAM_CAP/256) B200_STREAM_CASE(1, 1, STREAM_CAP)
+	else if(max_len <= STREAM_CAP/128) B200_STREAM_CASE(2, 1, STREAM_CAP)
+	else if(max_len <= STREAM_CAP/64) B200_STREAM_CASE(4, 1, STREAM_CAP)
+	else B200_STREAM_CASE(8, 1, STREAM_CAP)
 #undef B200_STREAM_CASE
 	B200_LAUNCHED();
 }

@@ -146,12 +146,13 @@ struct DistOps : public KrylovOps {
 		if(M) prec_apply(*M, r, z);
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
-	void dots(int nd, const double *const *a, const double *const *b, double *out) override {
+	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
 		launch_multi_dot(n, nd, a, b, partial, dout, stream);
 		if(D->comm->world > 1)
 			B200_NCCL(g_nccl.AllReduce(dout.p, dout.p, nd, ncclFloat64, ncclSum, D->comm->comm, stream));
 		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
 		B200_CUDA(cudaStreamSynchronize(stream));
+		return dout.p;
 	}
 };
 

@@ -379,6 +379,12 @@ class GCR(_IterativeSolver):
         self.restart = n_restart
 
 
+class FGMRES(GCR):
+    """Flexible GMRES(m) proper (PETSc's -ksp_type fgmres): same iterates as GCR in exact arithmetic
+    (tests/solvers.hpp:108-110) at about half the orthogonalisation traffic."""
+    _name = "fgmres"
+
+
 # ---- per-kernel-class device timing (b200_profile_*) ----
 KERNEL_CLASSES = ["factor_lower", "factor_upper", "factor_init", "diag_invert", "tri_lower",
                   "tri_upper", "spmv", "other"]

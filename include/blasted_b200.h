@@ -192,7 +192,9 @@ typedef struct b200_solve_info {
 } b200_solve_info;
 
 /** solver: "bicgstab" (tests/solvers.cpp:140-244), "gcr" (:252-352, == FGMRES in exact
- *  arithmetic, tests/solvers.hpp:108-110), "richardson" (:90-133).  Host b/x. */
+ *  arithmetic, tests/solvers.hpp:108-110), "richardson" (:90-133), and "fgmres": flexible
+ *  GMRES(restart) proper (right-preconditioned, classical Gram-Schmidt, Givens rotations; what
+ *  PETSc's -ksp_type fgmres runs around the reference; iters = inner iterations).  Host b/x. */
 int b200_solve_host(const char *solver, const b200_mat *A, b200_prec *M, const double *b, double *x,
                     double tol, int maxiter, int restart, b200_solve_info *info);
 /** Device b/x. */

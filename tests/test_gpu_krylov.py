@@ -74,3 +74,25 @@ def test_richardson_and_noprec():
     x = np.zeros(m.dim)
     info = sol.solve(b, x)
     assert info.iters > 0 and np.isfinite(info.resnorm)
+
+
+@pytest.mark.parametrize("key", ["2dcyl1_bsr4", "2dcyl1_csr", "msc00726_csr"])
+@pytest.mark.parametrize("prec", ["seqilu0", "level_sgs"])
+def test_fgmres_matches_gcr(key, prec):
+    """FGMRES(30) proper and the reference's GCR(30) are the same method in exact arithmetic
+    (tests/solvers.hpp:108-110): same iteration count (within 5 %), both solve the system."""
+    gm, m = golden_matrices(), case(key)
+    b = gm[key.split("_")[0] + "_b"]
+    view = bb.SRMatrixView(m)
+    p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES[prec], bs=m.bs, blockstorage=1 if m.rowmajor else 0))
+    p.compute()
+    its = {}
+    for name, cls in (("gcr", bb.GCR), ("fgmres", bb.FGMRES)):
+        sol = cls(view, p, 30)
+        sol.setParams(1e-10, 2000)
+        x = np.zeros(m.dim)
+        info = sol.solve(b, x)
+        its[name] = info.iters
+        assert np.linalg.norm(b - orc().spmv(m, x))/np.linalg.norm(b) < 5e-10
+    assert abs(its["fgmres"] - its["gcr"]) <= max(1, int(np.ceil(0.05*its["gcr"]))), its
