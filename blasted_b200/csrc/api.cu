@@ -399,6 +399,8 @@ void b200_prec_destroy(b200_prec *p)
 	if(!p) return;
 	if(p->p.ev0) cudaEventDestroy(p->p.ev0);
 	if(p->p.ev1) cudaEventDestroy(p->p.ev1);
+	for(void *g : p->p.level_graph) if(g) cudaGraphExecDestroy((cudaGraphExec_t)g);
+	if(p->p.cap_stream) cudaStreamDestroy(p->p.cap_stream);
 	delete p;
 }
 

@@ -203,7 +203,10 @@ void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st);
 
 // factor.cu
 void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st);
-void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st);
+/// Block factors: writes the initial guess into `ilu` and (INIT_F_ORIGINAL / INIT_F_SGS, dinv != null)
+/// the inverses of the initial diagonal blocks into the compact array `dinv`.
+void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, double *dinv,
+                      cudaStream_t st);
 /// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
 /// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
 /// `all_upper`: also recompute the upper entries without products (needed once when the initial
@@ -281,6 +284,10 @@ struct Prec {
 	int factor_sweeps_done = 0;         ///< sweeps used by the last compute (exact variants iterate)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double compute_ms = 0, apply_ms = 0;
+	// level-scheduled applies replayed as CUDA graphs (precond.cu::run_level_graph)
+	DevBuf<double> lev_r, lev_z;
+	cudaStream_t cap_stream = nullptr;
+	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
 
 	int dim() const { return A->nbrows*A->bs; }
 };

@@ -173,7 +173,7 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
                   const double *__restrict__ avals, const int *__restrict__ posptr,
                   const int *__restrict__ lowerp, const int *__restrict__ upperp,
                   const double *__restrict__ scale, double *ilu, double *__restrict__ resout,
-                  int *__restrict__ changed)
+                  int *__restrict__ changed, double *__restrict__ dinv_out)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
@@ -182,6 +182,9 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 	const int g = lane / BS, r = lane - g*BS;
 	const long long entry = warp*GPW + g;
 	double res = 0;
+	double sum[BS];
+#pragma unroll
+	for(int c = 0; c < BS; c++) sum[c] = 0;
 	bool active = (g < GPW) && (entry < nnzb);
 	int row = 0, col = 0;
 	bool lower = false;
@@ -193,7 +196,6 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 		if(PHASE == PH_UPPER && lower) active = false;
 	}
 	if(active) {
-		double sum[BS];
 		BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 		if(SCALE) {
 			// scaleBlock: val(i,j) *= scale[brow*bs+i]*scale[bcol*bs+j]  (kernels_ilu0_factorize.hpp:61-69)
@@ -257,6 +259,25 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 				BlkIO<BS>::store_row(op, r, sum);
 		}
 	}
+	if((MODE == MODE_INIT_ORIG || MODE == MODE_INIT_SGS) && dinv_out) {
+		// the initial guess of a diagonal block is the (scaled) A_ii held row-wise in `sum`: invert
+		// it into the compact array right here instead of re-reading it in a separate pass
+		const bool isdiag = active && row == col;
+		if(__any_sync(0xffffffffu, isdiag)) {
+			double d[BS2], e[BS], x[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++)
+#pragma unroll
+				for(int m = 0; m < BS; m++)
+					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], min(g*BS + m, 31));
+			if(isdiag) {
+#pragma unroll
+				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
+				solve_right<BS>(d, e, x);
+				BlkIO<BS>::store_row(dinv_out + (size_t)row*BS2, r, x);
+			}
+		}
+	}
 	if(MODE == MODE_RESIDUAL) {
 #pragma unroll
 		for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
@@ -298,8 +319,108 @@ __device__ __forceinline__ bool row_differs(const double *blk, const int r, cons
 }
 
 template <int BS, bool SCALE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
+                        const int *__restrict__ browind, const double *__restrict__ avals,
+                        const int *__restrict__ posptr, const int2 *__restrict__ pairs,
+                        const double *__restrict__ scale, const double *__restrict__ dinv,
+                        double *ilu, int *__restrict__ changed)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const long long stride = (((long long)gridDim.x*blockDim.x) >> 5)*GPW;
+	const bool lanevalid = g < GPW;
+
+	// Three-stage software pipeline over this group's items t, t+stride, ...:
+	//   stage M: indices {entry, col} of item i+2        (8 B, from the packed list)
+	//   stage D: data of item i+1 - row r of A_ij, row r of U_jj^-1, the product range
+	//   stage C: products (rare), L = S * U_jj^-1, single final store of item i
+	// so the loads of the next item are in flight while the current one is computed and stored.
+	// Every lane runs the same instruction stream (the group products are warp collectives);
+	// lanes without an item work on zeros and store nothing.
+	long long t = warp*GPW + g;
+	int2 meta1 = make_int2(-1, -1), meta2 = make_int2(-1, -1);
+	if(lanevalid && t < nlower) meta1 = __ldg(lmeta + t);
+	if(lanevalid && t + stride < nlower) meta2 = __ldg(lmeta + t + stride);
+
+	double arow[BS], drow[BS];
+	int ps = 0, pe = 0;
+#pragma unroll
+	for(int c = 0; c < BS; c++) { arow[c] = 0; drow[c] = 0; }
+	if(meta1.x >= 0) {
+		BlkIO<BS>::template load_row<false>(avals + (size_t)meta1.x*BS2, r, arow);
+		BlkIO<BS>::template load_row<false>(dinv + (size_t)meta1.y*BS2, r, drow);
+		ps = __ldg(posptr + meta1.x); pe = __ldg(posptr + meta1.x + 1);
+	}
+	int2 meta = meta1;
+
+	const long long niter = (nlower + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		// stage M for item it+2
+		int2 meta3 = make_int2(-1, -1);
+		if(lanevalid && t + 2*stride < nlower) meta3 = __ldg(lmeta + t + 2*stride);
+		// stage D for item it+1
+		double arow_n[BS], drow_n[BS];
+		int ps_n = 0, pe_n = 0;
+#pragma unroll
+		for(int c = 0; c < BS; c++) { arow_n[c] = 0; drow_n[c] = 0; }
+		if(meta2.x >= 0) {
+			BlkIO<BS>::template load_row<false>(avals + (size_t)meta2.x*BS2, r, arow_n);
+			BlkIO<BS>::template load_row<false>(dinv + (size_t)meta2.y*BS2, r, drow_n);
+			ps_n = __ldg(posptr + meta2.x); pe_n = __ldg(posptr + meta2.x + 1);
+		}
+
+		// stage C for item it
+		const bool active = meta.x >= 0;
+		const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
+		double sum[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] = arow[c];
+		if(SCALE && active) {
+			const int row = __ldg(browind + entry);
+			const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+		}
+		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
+		for(int k = 0; k < nk; k++) {
+			const bool has = ps + k < pe;
+			int2 pr = make_int2(0, 0);
+			if(has) pr = __ldg(pairs + ps + k);
+			double lr[BS], ur[BS];
+#pragma unroll
+			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
+			if(has) {
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
+			}
+			group_mul_sub<BS>(sum, lr, ur, g*BS);
+		}
+		double out[BS];
+		group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
+		if(active) {
+			double *op = ilu + (size_t)entry*BS2;
+			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
+			BlkIO<BS>::store_row(op, r, out);                            // single final store
+		}
+
+		// advance the pipeline
+		meta = meta2; meta2 = meta3;
+#pragma unroll
+		for(int c = 0; c < BS; c++) { arow[c] = arow_n[c]; drow[c] = drow_n[c]; }
+		ps = ps_n; pe = pe_n;
+		t += stride;
+	}
+}
+
+// The same launch without the data stage of the pipeline: for bs = 5 the second set of row
+// registers costs more in occupancy/spills than the overlap gains.
+template <int BS, bool SCALE>
+__global__ void __launch_bounds__(256, 4)
+block_ilu0_lower_simple_kernel(const long long nlower, const int2 *__restrict__ lmeta,
                         const int *__restrict__ browind, const double *__restrict__ avals,
                         const int *__restrict__ posptr, const int2 *__restrict__ pairs,
                         const double *__restrict__ scale, const double *__restrict__ dinv,
@@ -506,14 +627,16 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 	const int4 *uplist = all_upper ? pl.umeta.p : pl.uwork.p;
 	constexpr int GPW = 32/BS;
 	const long long per_cta = 8*GPW;
+	static const bool force_simple = getenv("B200_LOWER_SIMPLE") != nullptr;   // A/B switch (development)
+	const bool pipelined = (BS <= 4) && !force_simple;
 	if(pl.nlower > 0) {
 		ProfScope ps(KC_FACTOR_LOWER, st);
 		if(scale) {
-			auto k = block_ilu0_lower_kernel<BS,true>;
+			auto k = pipelined ? block_ilu0_lower_kernel<BS,true> : block_ilu0_lower_simple_kernel<BS,true>;
 			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
 				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
 		} else {
-			auto k = block_ilu0_lower_kernel<BS,false>;
+			auto k = pipelined ? block_ilu0_lower_kernel<BS,false> : block_ilu0_lower_simple_kernel<BS,false>;
 			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
 				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
 		}
@@ -547,7 +670,7 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 
 template <int BS, int PHASE, int MODE>
 static void launch_block(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
-                         double *resout, int *changed, cudaStream_t st)
+                         double *resout, int *changed, double *dinv_out, cudaStream_t st)
 {
 	constexpr int GPW = 32/BS;
 	const long long nwarps = (A.nnzb + GPW - 1)/GPW;
@@ -556,27 +679,28 @@ static void launch_block(const Mat& A, const IluPattern *pl, const double *scale
 		*up = pl ? pl->upperp.p : nullptr;
 	if(scale)
 		block_ilu0_kernel<BS,true,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed, dinv_out);
 	else
 		block_ilu0_kernel<BS,false,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);
+			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed, dinv_out);
 	B200_LAUNCHED();
 }
 
 template <int PHASE, int MODE>
 static void launch_any(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
-                       double *resout, int *changed, cudaStream_t st)
+                       double *resout, int *changed, cudaStream_t st, double *dinv_out = nullptr)
 {
 	if(A.nnzb == 0) return;
 	switch(A.bs) {
 	case 1: launch_scalar<PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
-	case 4: launch_block<4,PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
-	case 5: launch_block<5,PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
+	case 4: launch_block<4,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
+	case 5: launch_block<5,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
 	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
 	}
 }
 
-void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, cudaStream_t st)
+void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, double *dinv,
+                      cudaStream_t st)
 {
 	if(fact_init == B200_INIT_F_NONE) return;
 	ProfScope ps(KC_FACTOR_INIT, st);
@@ -587,9 +711,9 @@ void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *
 		return;
 	}
 	if(fact_init == B200_INIT_F_SGS)
-		launch_any<PH_ALL,MODE_INIT_SGS>(A, nullptr, scale, ilu, nullptr, nullptr, st);
+		launch_any<PH_ALL,MODE_INIT_SGS>(A, nullptr, scale, ilu, nullptr, nullptr, st, dinv);
 	else
-		launch_any<PH_ALL,MODE_INIT_ORIG>(A, nullptr, scale, ilu, nullptr, nullptr, st);
+		launch_any<PH_ALL,MODE_INIT_ORIG>(A, nullptr, scale, ilu, nullptr, nullptr, st, dinv);
 }
 
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,

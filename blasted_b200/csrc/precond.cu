@@ -91,14 +91,19 @@ void prec_compute(Prec& P, double precinfo[6])
 			launch_scaling_vector(A, P.scale, st);
 			scale = P.scale;
 		}
-		if(scalar) scalar_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
-		else launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, st);
-		// compact inverses of the (initial) diagonal blocks, kept current by the upper launches
+		// compact inverses of the diagonal blocks: written by the initialisation, kept current by
+		// the upper launches of the sweeps
 		double *dinv = nullptr;
 		if(A.bs > 1) {
 			if(!P.dinv.p) P.dinv.alloc((size_t)A.nbrows*A.bs*A.bs);
 			dinv = P.dinv;
-			launch_invert_diag_blocks(A, P.ilu, A.diagind, dinv, true, st);
+		}
+		if(scalar) scalar_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
+		else {
+			launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, dinv, st);
+			const bool fused = (P.s.fact_inittype == B200_INIT_F_ORIGINAL ||
+			                    P.s.fact_inittype == B200_INIT_F_SGS);
+			if(!fused) launch_invert_diag_blocks(A, P.ilu, A.diagind, dinv, true, st);
 		}
 
 		// Async_Level_ILU0 (scalar) passes `threadedfactor`=true into the compute_info slot
@@ -167,6 +172,55 @@ void prec_compute(Prec& P, double precinfo[6])
 
 // ------------------------------------------------------------------ level-scheduled sweeps
 
+/// Runs `body` (a sequence of per-level launches reading P.lev_r and writing P.lev_z) as a CUDA
+/// graph: thousands of tiny dependent launches are the whole cost of a level-scheduled solve, and a
+/// graph replays them without per-launch driver work.  Captured once per preconditioner and `slot`
+/// on a private stream (the legacy default stream cannot be captured), replayed on the handle's
+/// stream; input/output go through fixed internal buffers so the kernel arguments never change.
+template <typename Body>
+static void run_level_graph(Prec& P, int slot, const double *r, double *z, Body body)
+{
+	const long long n = P.A->dim();
+	cudaStream_t st = P.stream;
+	if(!P.lev_r.p) { P.lev_r.alloc(n); P.lev_z.alloc(n); }
+	B200_CUDA(cudaMemcpyAsync(P.lev_r, r, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+	if(P.levels.nlevels > 16384) {
+		// degenerate schedules (the reference's contiguous levels on a stencil matrix give ~N
+		// levels): a graph of that size is pointless, launch directly
+		body();
+		B200_CUDA(cudaMemcpyAsync(z, P.lev_z, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+		return;
+	}
+	if(!P.level_graph[slot]) {
+		if(!P.cap_stream) B200_CUDA(cudaStreamCreateWithFlags(&P.cap_stream, cudaStreamNonBlocking));
+		B200_CUDA(cudaStreamSynchronize(st));
+		const bool prof = g_prof.enabled;
+		g_prof.enabled = false;                 // no timing events inside a capture
+		cudaStream_t saved = P.stream;
+		P.stream = P.cap_stream;
+		cudaGraph_t graph = nullptr;
+		try {
+			B200_CUDA(cudaStreamBeginCapture(P.cap_stream, cudaStreamCaptureModeThreadLocal));
+			body();
+			B200_CUDA(cudaStreamEndCapture(P.cap_stream, &graph));
+		} catch(...) {
+			cudaStreamEndCapture(P.cap_stream, &graph);
+			if(graph) cudaGraphDestroy(graph);
+			P.stream = saved; g_prof.enabled = prof;
+			throw;
+		}
+		P.stream = saved; g_prof.enabled = prof;
+		cudaGraphExec_t exec = nullptr;
+		const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if(e != cudaSuccess) throw Error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+		P.level_graph[slot] = exec;
+	}
+	B200_CUDA(cudaGraphLaunch((cudaGraphExec_t)P.level_graph[slot], st));
+	g_launches.fetch_add(2*(long long)P.levels.nlevels, std::memory_order_relaxed);
+	B200_CUDA(cudaMemcpyAsync(z, P.lev_z, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+}
+
 static void level_sweep(Prec& P, TriKind kind, TriArgs a, bool backward)
 {
 	const Mat& A = *P.A;
@@ -228,11 +282,13 @@ void prec_apply(Prec& P, const double *r, double *z)
 	}
 	else if(type == B200_LEVEL_SGS) {
 		// Level_SGS::apply, solverops_levels_sgs.cpp:54-87,160-189
-		TriArgs a; a.vals = A.vals; a.dinv = P.dinv;
-		a.rhs = r; a.x = P.ytemp;
-		level_sweep(P, TRI_SGS_FWD, a, false);
-		a.rhs = P.ytemp; a.x = z;
-		level_sweep(P, TRI_SGS_BWD, a, true);
+		run_level_graph(P, 0, r, z, [&] {
+			TriArgs a; a.vals = A.vals; a.dinv = P.dinv;
+			a.rhs = P.lev_r; a.x = P.ytemp;
+			level_sweep(P, TRI_SGS_FWD, a, false);
+			a.rhs = P.ytemp; a.x = P.lev_z;
+			level_sweep(P, TRI_SGS_BWD, a, true);
+		});
 	}
 	else if(P.is_ilu) {
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
@@ -253,10 +309,12 @@ void prec_apply(Prec& P, const double *r, double *z)
 			// triangular solves of the sequential variants
 			if(!P.uses_levels && P.s.apply_inittype == B200_INIT_A_NONE)
 				throw Error(" scalar_ilu0_apply: Invalid init type!");
-			aL.rhs = r; aL.rscale = scale; aL.x = P.ytemp;
-			level_sweep(P, TRI_ILU_LOWER, aL, false);
-			aU.rhs = P.ytemp; aU.rscale = nullptr; aU.x = z;
-			level_sweep(P, TRI_ILU_UPPER, aU, true);
+			run_level_graph(P, 0, r, z, [&] {
+				aL.rhs = P.lev_r; aL.rscale = scale; aL.x = P.ytemp;
+				level_sweep(P, TRI_ILU_LOWER, aL, false);
+				aU.rhs = P.ytemp; aU.rscale = nullptr; aU.x = P.lev_z;
+				level_sweep(P, TRI_ILU_UPPER, aU, true);
+			});
 		}
 		else {
 			// scalar_ilu0_apply / block_ilu0_apply, solverops_ilu0.cpp:56-148,240-321.
