@@ -156,9 +156,16 @@ struct IluPattern {
 	DevBuf<int4> suall, suwork;          ///< per upper entry: {entry, pos begin, pos end, dest};
 	                                     ///< dest = index into the U values, or ~row for a diagonal
 	DevBuf<int2> spairs;                 ///< products re-indexed into the split L / U value arrays
-	bool built = false;
+	DevBuf<int> lentry, uentry;          ///< split-only build (SGS): position in A of every L / U entry
+	bool built = false, split_built = false;
 };
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
+/// Scalar matrices: only the split CSR structure (lptr/lcol/uptr/ucol, lentry/uentry, part lengths),
+/// for sweeps over A itself (SGS); no ILU position lists.
+void build_split_csr(const Mat& A, IluPattern& pl, cudaStream_t st);
+/// lval[t] = vals[lentry[t]], uval[t] = vals[uentry[t]]
+void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
+                         cudaStream_t st);
 
 /// Values of the scalar ILU(0) factor in split form (see IluPattern)
 struct ScalarFactor {
@@ -177,7 +184,8 @@ void scalar_ilu0_gather(const Mat& A, const IluPattern& pl, const ScalarFactor& 
                         cudaStream_t st);
 
 // csrstream.cu
-enum StreamKind { STREAM_SPMV, STREAM_GEMV3, STREAM_TRI_LOWER, STREAM_TRI_UPPER };
+enum StreamKind { STREAM_SPMV, STREAM_GEMV3, STREAM_TRI_LOWER, STREAM_TRI_UPPER,
+                  STREAM_SGS_FWD, STREAM_SGS_BWD };
 struct StreamArgs {
 	const int *ptr = nullptr, *col = nullptr;     ///< CSR part (rows ptr[i]..ptr[i+1])
 	const double *val = nullptr;

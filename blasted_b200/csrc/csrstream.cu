@@ -82,7 +82,7 @@ csr_stream_kernel(const StreamArgs a)
 
 	// right-hand sides of this thread's rows: issued now, consumed at the end
 	double rhs[RPT];
-	if(KIND == STREAM_TRI_LOWER || KIND == STREAM_TRI_UPPER || KIND == STREAM_GEMV3) {
+	if(KIND != STREAM_SPMV) {
 #pragma unroll
 		for(int k = 0; k < RPT; k++) {
 			const int lr = (LPR > 1) ? tid/LPR : tid + k*256;
@@ -140,7 +140,9 @@ csr_stream_kernel(const StreamArgs a)
 			if(KIND == STREAM_SPMV) a.out[row] = sum;
 			else if(KIND == STREAM_GEMV3) a.out[row] = a.alpha*sum + rhs[k];
 			else if(KIND == STREAM_TRI_LOWER) a.out[row] = rhs[k] - sum;
-			else a.out[row] = (1.0/__ldg(a.diag + row))*(rhs[k] - sum);     // STREAM_TRI_UPPER
+			else if(KIND == STREAM_TRI_UPPER) a.out[row] = (1.0/__ldg(a.diag + row))*(rhs[k] - sum);
+			else if(KIND == STREAM_SGS_FWD) a.out[row] = __ldg(a.diag + row)*(rhs[k] - sum);   // diag = 1/a_ii
+			else a.out[row] = rhs[k] - __ldg(a.diag + row)*sum;                               // STREAM_SGS_BWD
 		}
 	}
 }
@@ -159,7 +161,7 @@ static void launch_kind(const StreamArgs& a, int max_len, cudaStream_t st)
 		constexpr int R = 256*P/L;                                                 \
 		csr_stream_kernel<KIND,L,P,C><<<div_up(nrows, R), 256, 0, st>>>(a);        \
 	}
-	const bool tri = (KIND == STREAM_TRI_LOWER || KIND == STREAM_TRI_UPPER);
+	const bool tri = (KIND != STREAM_SPMV && KIND != STREAM_GEMV3);
 	if(tri && small && max_len <= 3) B200_STREAM_CASE(1, 2, 1536)
 	else if(tri && small && max_len <= 7) B200_STREAM_CASE(1, 1, 1792)
 	else if(max_len <= STREAM_CAP/1024) B200_STREAM_CASE(1, 4, STREAM_CAP)
@@ -182,6 +184,8 @@ void launch_csr_stream(StreamKind kind, const StreamArgs& a, int max_len, cudaSt
 	case STREAM_GEMV3: launch_kind<STREAM_GEMV3>(a, max_len, st); break;
 	case STREAM_TRI_LOWER: launch_kind<STREAM_TRI_LOWER>(a, max_len, st); break;
 	case STREAM_TRI_UPPER: launch_kind<STREAM_TRI_UPPER>(a, max_len, st); break;
+	case STREAM_SGS_FWD: launch_kind<STREAM_SGS_FWD>(a, max_len, st); break;
+	case STREAM_SGS_BWD: launch_kind<STREAM_SGS_BWD>(a, max_len, st); break;
 	}
 }
 

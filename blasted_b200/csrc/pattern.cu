@@ -321,6 +321,95 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.built = true;
 }
 
+// ------------------------------------------------------------------ split CSR only (scalar SGS)
+
+__global__ void __launch_bounds__(256)
+split_entries_kernel(const long long nnz, const int *__restrict__ rowptr,
+                     const int *__restrict__ colind, const int *__restrict__ diagind,
+                     const int *__restrict__ rowind, const int *__restrict__ loff,
+                     int *__restrict__ lcol, int *__restrict__ ucol, int *__restrict__ lentry,
+                     int *__restrict__ uentry)
+{
+	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(j >= nnz) return;
+	const int row = rowind[j], col = colind[j];
+	const int rs = rowptr[row], dg = diagind[row], lo = loff[row];
+	if(j < dg) {
+		const int t = lo + (int)(j - rs);
+		lcol[t] = col; lentry[t] = (int)j;
+	} else if(j > dg) {
+		const int ui = (rs - lo - row) + (int)(j - dg - 1);
+		ucol[ui] = col; uentry[ui] = (int)j;
+	}
+}
+
+__global__ void gather_kernel(const long long n, const int *__restrict__ idx,
+                              const double *__restrict__ in, double *__restrict__ out)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(t < n) out[t] = in[idx[t]];
+}
+
+void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
+                         cudaStream_t st)
+{
+	if(pl.nlower > 0) {
+		gather_kernel<<<div_up(pl.nlower, 256), 256, 0, st>>>(pl.nlower, pl.lentry, vals, lval);
+		B200_LAUNCHED();
+	}
+	if(pl.nstrict > 0) {
+		gather_kernel<<<div_up(pl.nstrict, 256), 256, 0, st>>>(pl.nstrict, pl.uentry, vals, uval);
+		B200_LAUNCHED();
+	}
+}
+
+void build_split_csr(const Mat& A, IluPattern& pl, cudaStream_t st)
+{
+	const int n = A.nbrows;
+	const long long nnz = A.nnzb;
+	DevBuf<int> nl_row;
+	nl_row.alloc((size_t)n + 1);
+	pl.lptr.alloc((size_t)n + 1);
+	pl.uptr.alloc((size_t)n + 1);
+	lower_count_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, A.browptr, A.diagind, nl_row);
+	B200_LAUNCHED();
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, nl_row.p, pl.lptr.p, n + 1, st);
+	DevBuf<char> tmp;
+	tmp.alloc(tb);
+	B200_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nl_row.p, pl.lptr.p, n + 1, st));
+	g_launches.fetch_add(1);
+	int nl = 0;
+	B200_CUDA(cudaMemcpyAsync(&nl, pl.lptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	pl.nlower = nl;
+	pl.nupper = nnz - nl;
+	pl.nstrict = pl.nupper - n;
+	pl.lcol.alloc(std::max<long long>(pl.nlower, 1));
+	pl.lentry.alloc(std::max<long long>(pl.nlower, 1));
+	pl.ucol.alloc(std::max<long long>(pl.nstrict, 1));
+	pl.uentry.alloc(std::max<long long>(pl.nstrict, 1));
+	scalar_uptr_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, A.browptr, pl.lptr, pl.uptr);
+	B200_LAUNCHED();
+	if(nnz > 0) {
+		split_entries_kernel<<<div_up(nnz, 256), 256, 0, st>>>(nnz, A.browptr, A.bcolind, A.diagind,
+			A.browind, pl.lptr, pl.lcol, pl.ucol, pl.lentry, pl.uentry);
+		B200_LAUNCHED();
+	}
+	DevBuf<int> d_ml;
+	d_ml.alloc(2);
+	B200_CUDA(cudaMemsetAsync(d_ml, 0, 2*sizeof(int), st));
+	if(n > 0) {
+		part_max_len_kernel<<<std::min(div_up(n, 256), 148*8), 256, 0, st>>>(n, A.browptr, A.diagind, d_ml);
+		B200_LAUNCHED();
+	}
+	int h[2] = {0, 0};
+	B200_CUDA(cudaMemcpyAsync(h, d_ml, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	pl.max_lower_len = h[0]; pl.max_upper_len = h[1];
+	pl.split_built = true;
+}
+
 // ------------------------------------------------------------------ structural symmetry check
 
 __global__ void symmetry_check_kernel(const long long nnzb, const int *__restrict__ browptr,

@@ -64,7 +64,15 @@ void prec_compute(Prec& P, double precinfo[6])
 			P.ytemp.alloc(A.dim());
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
 			if(P.uses_levels) build_levels(A, P.levels, P.s.level_mode, st);
+			// scalar async SGS: sweeps run over a split copy of A (L part, strict U part) so that
+			// each sweep streams one contiguous array through the staged kernel (csrstream.cu)
+			if(type == B200_SGS && A.bs == 1 && stream_supported(A.max_row_len)) {
+				build_split_csr(A, P.pl, st);
+				P.sf.lval.alloc(std::max<long long>(P.pl.nlower, 1));
+				P.sf.uval.alloc(std::max<long long>(P.pl.nstrict, 1));
+			}
 		}
+		if(P.pl.split_built) gather_split_values(P.pl, A.vals, P.sf.lval, P.sf.uval, st);
 	}
 	else if(P.is_ilu) {
 		const bool scalar = (A.bs == 1);       // scalar factors live in split form (P.sf), see scalar_ilu.cu
@@ -272,13 +280,34 @@ void prec_apply(Prec& P, const double *r, double *z)
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
 		TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.row_begin = 0; a.row_end = A.nbrows;
 		a.rhs = r; a.x = P.ytemp; a.descending = false;
-		for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_SGS_FWD, a, st);
+		const bool split = P.pl.split_built;
+		StreamArgs sa;
+		if(split) {
+			sa.ptr = P.pl.lptr; sa.col = P.pl.lcol; sa.val = P.sf.lval; sa.x = P.ytemp; sa.out = P.ytemp;
+			sa.rhs = r; sa.diag = P.dinv; sa.row_end = A.nbrows;
+		}
+		for(int sw = 0; sw < P.s.napplysweeps; sw++) {
+			if(split) {
+				ProfScope ps(KC_TRI_LOWER, st);
+				launch_csr_stream(STREAM_SGS_FWD, sa, std::max(P.pl.max_lower_len, 1), st);
+			} else launch_tri_sweep(A, TRI_SGS_FWD, a, st);
+		}
 		if(ai == B200_INIT_A_JACOBI)
 			B200_CUDA(cudaMemcpyAsync(z, P.ytemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 		else if(ai == B200_INIT_A_ZERO)
 			B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
 		a.rhs = P.ytemp; a.x = z; a.descending = true;
-		for(int sw = 0; sw < P.s.napplysweeps; sw++) launch_tri_sweep(A, TRI_SGS_BWD, a, st);
+		if(split) {
+			sa = StreamArgs();
+			sa.ptr = P.pl.uptr; sa.col = P.pl.ucol; sa.val = P.sf.uval; sa.x = z; sa.out = z;
+			sa.rhs = P.ytemp; sa.diag = P.dinv; sa.row_end = A.nbrows; sa.descending = 1;
+		}
+		for(int sw = 0; sw < P.s.napplysweeps; sw++) {
+			if(split) {
+				ProfScope ps(KC_TRI_UPPER, st);
+				launch_csr_stream(STREAM_SGS_BWD, sa, std::max(P.pl.max_upper_len, 1), st);
+			} else launch_tri_sweep(A, TRI_SGS_BWD, a, st);
+		}
 	}
 	else if(type == B200_LEVEL_SGS) {
 		// Level_SGS::apply, solverops_levels_sgs.cpp:54-87,160-189

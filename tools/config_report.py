@@ -108,7 +108,7 @@ def report(title, m, nb=3, na=3, scale=False, sgs=False, levels=False, solve=Non
         p.set_sweeps(*solve)
         p.compute()
         bvec = view.apply(torch.ones(m.dim, dtype=torch.float64, device="cuda"))
-        for name, cls in (("BiCGSTAB", lambda: bb.BiCGSTAB(view, p)), ("GCR(30)", lambda: bb.GCR(view, p, 30))):
+        for name, cls in (("FGMRES(30)", lambda: bb.FGMRES(view, p, 30)), ("GCR(30)", lambda: bb.GCR(view, p, 30))):
             sol = cls(); sol.setParams(1e-8, 2000)
             xs = torch.zeros_like(bvec)
             info = sol.solve(bvec, xs)
@@ -120,10 +120,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     print(f"# Per-kernel throughput on the BASELINE configs ({torch.cuda.get_device_name(0)})")
     if "c1" in which:
-        report("C1 - 7-point Poisson 256^3, CSR", matgen.poisson3d(256), solve=(5, 10), levels=True)
+        report("C1 - 7-point Poisson 256^3, CSR", matgen.poisson3d(256), solve=(5, 5), levels=True, sgs=True)
     if "c2" in which:
         report("C2 - BSR bs=4, 1024x1024 cells (headline)", matgen.block_stencil((1024, 1024), 4, 20261020), sgs=True, solve=(3, 3))
     if "c3" in which:
         report("C3 - BSR bs=5, 128^3 cells", matgen.block_stencil((128, 128, 128), 5, 20261021), sgs=True, solve=(3, 3))
     if "c4" in which:
-        report("C4 - 27-point Poisson 192^3, CSR (scaled)", matgen.poisson3d(192, 27), scale=True, levels=True, solve=(10, 20))
+        report("C4 - 27-point Poisson 192^3, CSR (scaled)", matgen.poisson3d(192, 27), scale=True, levels=True, sgs=True, solve=(10, 20))
