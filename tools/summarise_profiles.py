@@ -15,11 +15,10 @@ CLASS = {"block_ilu0_lower": "factor_lower", "block_ilu0_upper": "factor_upper",
          "tri_block_kernel<5, 0": "tri_lower", "tri_block_kernel<5, 1": "tri_upper"}
 traffic = {}
 for w in ("c2", "c3s", "p128"):
-    rep = os.path.join(ROOT, "gpurun_out", f"prof_{w}_{R}.ncu-rep")
-    if not os.path.exists(rep):
+    rawf = os.path.join(ROOT, "gpurun_out", f"raw_{w}_{R}.csv")
+    if not os.path.exists(rawf):
         continue
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = list(csv.reader(open(rawf).read().splitlines()))
     hdr, units = rows[0], rows[1]
     with open(os.path.join(OUT, f"ncu_{w}_{R}.csv"), "w") as f:
         wr = csv.writer(f)
@@ -34,7 +33,7 @@ for w in ("c2", "c3s", "p128"):
             if w == "c2":
                 name = r[hdr.index("Kernel Name")]
                 for key, cls in CLASS.items():
-                    if key in name and "<4" in name or (key in name and key.startswith("block")):
+                    if key in name:
                         def gb(x, u):
                             v = float(x.replace(",", ""))
                             return v*{"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
