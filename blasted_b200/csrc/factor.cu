@@ -23,12 +23,12 @@
  * L entries of the same sweep (the reference gets the same effect from processing a row's entries
  * in order).
  *
- * Mapping.  Scalar: a group of LPR lanes per row, one entry per lane.  Block: a group of bs lanes
- * per stored block ("entry-parallel", row index from browind), lane r owns row r of the block in
- * registers; partner blocks are broadcast loads; right-division by U_jj is a register-resident
- * bs x bs elimination with partial pivoting done redundantly per lane (no shuffles, no shared
- * memory).  All of it is HBM/L2-bound: algorithmic bytes per sweep, scalar 32 nnz + 8 npos + 8 N,
- * block nnzb (24 b^2 + 8) + 8 npos + 8 N.
+ * Mapping (blocks; the scalar factorisation is scalar_ilu.cu).  A group of bs lanes per stored
+ * block ("entry-parallel", packed per-phase work lists from pattern.cu), lane r owns row r of the
+ * block in registers; products stream the partner's rows through warp shuffles
+ * (blockops.cuh::group_mul_sub); U_jj^-1 comes from the compact array `dinv`, which the upper launch
+ * refreshes with a register-resident bs x bs elimination with partial pivoting (solve_right).
+ * All of it is HBM/L2-bound; algorithmic bytes per launch are listed in DESIGN.md section 3.
  */
 #include "common.cuh"
 #include "blockops.cuh"
@@ -66,101 +66,10 @@ void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st)
 	B200_LAUNCHED();
 }
 
-// ------------------------------------------------------------------ scalar ILU(0)
+// (the scalar factorisation lives in scalar_ilu.cu)
 
 enum { PH_ALL = 0, PH_LOWER = 1, PH_UPPER = 2 };
 enum { MODE_SWEEP = 0, MODE_RESIDUAL = 1, MODE_INIT_SGS = 2, MODE_INIT_ORIG = 3 };
-
-/// One (partial) asynchronous sweep, or the residual, or an initialisation, of scalar ILU(0).
-template <int LPR, bool SCALE, int PHASE, int MODE>
-__global__ void __launch_bounds__(256)
-scalar_ilu0_kernel(const int nrows, const int *__restrict__ rowptr, const int *__restrict__ colind,
-                   const int *__restrict__ diagind, const double *__restrict__ avals,
-                   const int *__restrict__ posptr, const int *__restrict__ lowerp,
-                   const int *__restrict__ upperp, const double *__restrict__ scale,
-                   double *ilu, double *__restrict__ resout, int *__restrict__ changed)
-{
-	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-	const int row = (int)(tid / LPR);
-	const int lane = (int)(tid % LPR);
-	double res = 0;
-	if(row < nrows) {
-		const int s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-		const double srow = SCALE ? __ldg(scale + row) : 1.0;
-		for(int j = s + lane; j < e; j += LPR) {
-			const int col = __ldg(colind + j);
-			const bool lower = row > col;
-			if(PHASE == PH_LOWER && !lower) continue;
-			if(PHASE == PH_UPPER && lower) continue;
-			double sum = __ldg(avals + j);
-			if(SCALE) { sum *= srow; sum *= __ldg(scale + col); }
-
-			if(MODE == MODE_INIT_ORIG) { ilu[j] = sum; continue; }
-			if(MODE == MODE_INIT_SGS) {
-				// L' = L D^-1 on the (scaled) matrix: async_ilu_factor.cpp:110-133; the scaled
-				// diagonal is a_cc*s_c*s_c (the reference indexes `scale` out of bounds there)
-				if(lower) {
-					const double sc = SCALE ? __ldg(scale + col) : 1.0;
-					const double dg = __ldg(avals + __ldg(diagind + col));
-					sum *= SCALE ? 1.0/(dg*sc*sc) : 1.0/dg;
-				}
-				ilu[j] = sum;
-				continue;
-			}
-
-			const int ps = __ldg(posptr + j), pe = __ldg(posptr + j + 1);
-			for(int k = ps; k < pe; k++)
-				sum = fma(-ld_iter(ilu + __ldg(lowerp + k)), ld_iter(ilu + __ldg(upperp + k)), sum);
-
-			if(MODE == MODE_RESIDUAL) {
-				if(lower) sum -= ld_iter(ilu + j) * ld_iter(ilu + __ldg(diagind + col));
-				else sum -= ld_iter(ilu + j);
-				res += fabs(sum);
-			} else {
-				if(lower) sum = sum / ld_iter(ilu + __ldg(diagind + col));
-				if(changed && ld_iter(ilu + j) != sum) *changed = 1;
-				ilu[j] = sum;                                   // single final store
-			}
-		}
-	}
-	if(MODE == MODE_RESIDUAL) {
-#pragma unroll
-		for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
-		__shared__ double wsum[8];
-		const int w = threadIdx.x >> 5;
-		if((threadIdx.x & 31) == 0) wsum[w] = res;
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			double t = 0;
-			for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
-			atomicAdd(resout, t);
-		}
-	}
-}
-
-template <int PHASE, int MODE>
-static void launch_scalar(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
-                          double *resout, int *changed, cudaStream_t st)
-{
-	const int n = A.nbrows;
-	const double avg = A.avg_row_len;
-	const int *pp = pl ? pl->posptr.p : nullptr, *lp = pl ? pl->lowerp.p : nullptr,
-		*up = pl ? pl->upperp.p : nullptr;
-#define B200_SC_CASE(L)                                                                             \
-	{                                                                                               \
-		const int grid = div_up((long long)n*L, 256);                                               \
-		if(scale) scalar_ilu0_kernel<L,true,PHASE,MODE><<<grid,256,0,st>>>(n, A.browptr, A.bcolind,   \
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);                            \
-		else scalar_ilu0_kernel<L,false,PHASE,MODE><<<grid,256,0,st>>>(n, A.browptr, A.bcolind,       \
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed);                            \
-	}
-	if(avg <= 5) B200_SC_CASE(4)
-	else if(avg <= 12) B200_SC_CASE(8)
-	else if(avg <= 24) B200_SC_CASE(16)
-	else B200_SC_CASE(32)
-#undef B200_SC_CASE
-	B200_LAUNCHED();
-}
 
 // ------------------------------------------------------------------ block ILU(0)
 
@@ -692,7 +601,6 @@ static void launch_any(const Mat& A, const IluPattern *pl, const double *scale, 
 {
 	if(A.nnzb == 0) return;
 	switch(A.bs) {
-	case 1: launch_scalar<PHASE,MODE>(A, pl, scale, ilu, resout, changed, st); break;
 	case 4: launch_block<4,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
 	case 5: launch_block<5,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
 	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));

@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product library and the oracle are build artefacts (git-ignored): build them when absent
+    # (nvcc cross-compiles without a GPU; on the GPU box the prebuilt files travel with the repo)
+    lib = os.path.join(ROOT, "blasted_b200", "libblasted_b200.so")
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu():
