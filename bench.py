@@ -142,6 +142,12 @@ def cpu_step_time(m, steps, warmup, nbuild, napply):
     r = np.random.default_rng(SEED).standard_normal(m.dim)
     if have_ref():
         R = ref()
+        # all host threads it can use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except Exception:
+            ncpu = os.cpu_count() or 1
+        R.set_num_threads(ncpu)
         cores = R.num_threads()
         p = R.prec(m, "ilu0", nbuildsweeps=nbuild, napplysweeps=napply, thread_chunk_size=128,
                    fact_init="init_original", apply_init="init_jacobi")
