@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblasted_b200.so")
+# B200_LIB: development override (A/B of two builds inside one GPU call)
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libblasted_b200.so")
 
 
 class Settings(C.Structure):

@@ -110,12 +110,21 @@ tri_block_kernel(const TriDev a)
 	const int nrows = a.row_end - a.row_begin;
 	const bool valid = (g < GPW) && (t < nrows);
 	int row = 0, d = 0;
-	double acc = 0;
+	double acc = 0, rhs = 0;
+	double dr[BS];
+#pragma unroll
+	for(int c = 0; c < BS; c++) dr[c] = 0;
 	if(valid) {
 		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
 		row = a.rows ? __ldg(a.rows + idx) : idx;
 		const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
 		d = __ldg(a.diagind + row);
+		// everything that depends only on the row is requested before the block loop
+		rhs = __ldg(a.rhs + (size_t)row*BS + r);
+		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
+		if(KIND != TRI_ILU_LOWER)
+			// compact inverted diagonal blocks: U_ii^-1 (ILU) or D_i^-1 of A (SGS, relaxation)
+			BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
 		int js, je;
 		part_range<KIND>(s, d, e, js, je);
 #pragma unroll 2
@@ -129,22 +138,11 @@ tri_block_kernel(const TriDev a)
 			for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
 		}
 	}
-	double rhs = 0;
-	if(valid) {
-		rhs = __ldg(a.rhs + (size_t)row*BS + r);
-		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
-	}
 	double out;
 	if(KIND == TRI_ILU_LOWER) out = rhs - acc;
 	else {
 		// multiply a bs-vector held one entry per lane by a bs x bs block: t_c via shuffles
 		const double tv = (KIND == TRI_SGS_BWD) ? acc : rhs - acc;
-		double dr[BS];
-#pragma unroll
-		for(int c = 0; c < BS; c++) dr[c] = 0;
-		if(valid)
-			// compact inverted diagonal blocks: U_ii^-1 (ILU) or D_i^-1 of A (SGS, relaxation)
-			BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
 		double prod = 0;
 #pragma unroll
 		for(int c = 0; c < BS; c++) {

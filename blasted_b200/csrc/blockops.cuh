@@ -27,8 +27,17 @@ __device__ __forceinline__ void ld256_nc(const double *p, double &a, double &b, 
 {
 	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
-/// data other CTAs may be rewriting during this launch (the chaotic iterate): read at L2
+/// data other CTAs may be rewriting during this launch (the chaotic iterate): read at L2.
+/// Relaxed: not `volatile`, no memory clobber, so the compiler may batch these gathers with the
+/// surrounding loads (more requests in flight); chaotic iteration does not care which of the
+/// concurrently written values a gather observes.
 __device__ __forceinline__ void ld256_cg(const double *p, double &a, double &b, double &c, double &d)
+{
+	asm("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+	    : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+/// same load, ordered against the surrounding stores (read-before-overwrite comparisons)
+__device__ __forceinline__ void ld256_cg_ordered(const double *p, double &a, double &b, double &c, double &d)
 {
 	asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
 	             : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
@@ -54,6 +63,11 @@ struct BlkIO {
 	{
 #pragma unroll
 		for(int c = 0; c < BS; c++) v[c] = ld1<ITER>(blk + c*BS + r);
+	}
+	static __device__ __forceinline__ void load_row_ordered(const double *blk, const int r, double (&v)[BS])
+	{
+#pragma unroll
+		for(int c = 0; c < BS; c++) v[c] = *((const volatile double*)(blk + c*BS + r));
 	}
 	static __device__ __forceinline__ void store_row(double *blk, const int r, const double (&v)[BS])
 	{
@@ -97,6 +111,10 @@ struct BlkIO<4> {
 	{
 		if(ITER) ld256_cg(blk + 4*r, v[0], v[1], v[2], v[3]);
 		else ld256_nc(blk + 4*r, v[0], v[1], v[2], v[3]);
+	}
+	static __device__ __forceinline__ void load_row_ordered(const double *blk, const int r, double (&v)[4])
+	{
+		ld256_cg_ordered(blk + 4*r, v[0], v[1], v[2], v[3]);
 	}
 	static __device__ __forceinline__ void store_row(double *blk, const int r, const double (&v)[4])
 	{

@@ -220,7 +220,7 @@ template <int BS>
 __device__ __forceinline__ bool row_differs(const double *blk, const int r, const double (&v)[BS])
 {
 	double cur[BS];
-	BlkIO<BS>::template load_row<true>(blk, r, cur);
+	BlkIO<BS>::load_row_ordered(blk, r, cur);        // must precede the overwrite that follows
 	bool ch = false;
 #pragma unroll
 	for(int c = 0; c < BS; c++) ch |= (cur[c] != v[c]);
