@@ -368,7 +368,7 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z)
 
 int b200_prec_apply_relax(b200_prec *p, const double *d_b, double *d_x, int maxits)
 {
-	return guarded([&] { prec_apply_relax(p->p, d_b, d_x, maxits); });
+	return guarded([&] { prec_apply_relax(p->p, d_b, d_x, maxits > 0 ? maxits : p->p.maxits); });
 }
 
 int b200_prec_apply_relax_host(b200_prec *p, const double *b, double *x, int maxits)
@@ -379,10 +379,17 @@ int b200_prec_apply_relax_host(b200_prec *p, const double *b, double *x, int max
 		P.hr.alloc(n); P.hz.alloc(n);
 		B200_CUDA(cudaMemcpyAsync(P.hr, b, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
 		B200_CUDA(cudaMemcpyAsync(P.hz, x, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
-		prec_apply_relax(P, P.hr, P.hz, maxits);
+		prec_apply_relax(P, P.hr, P.hz, maxits > 0 ? maxits : P.maxits);
 		B200_CUDA(cudaMemcpyAsync(x, P.hz, n*sizeof(double), cudaMemcpyDeviceToHost, P.stream));
 		B200_CUDA(cudaStreamSynchronize(P.stream));
 	});
+}
+
+int b200_prec_set_apply_params(b200_prec *p, double rtol, double atol, double dtol, int ctol, int maxits)
+{
+	Prec& P = p->p;
+	P.rtol = rtol; P.atol = atol; P.dtol = dtol; P.ctol = ctol != 0; P.maxits = maxits;
+	return 0;
 }
 
 int b200_prec_dim(const b200_prec *p) { return p->p.dim(); }

@@ -141,6 +141,39 @@ __global__ void vec_scal_kernel(const long long n, const double alpha, const dou
 	if(i < n) out[i] = alpha*in[i];
 }
 
+__global__ void __launch_bounds__(256)
+update_diffnorm_kernel(const long long n, const double *__restrict__ xtemp, double *x,
+                       double *__restrict__ out)
+{
+	double acc = 0;
+	for(long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n;
+	    i += (long long)gridDim.x*blockDim.x)
+	{
+		const double t = xtemp[i], d = t - x[i];
+		acc = fma(d, d, acc);
+		x[i] = t;
+	}
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+	__shared__ double sm[8];
+	if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		double t = 0;
+		for(int i = 0; i < 8; i++) t += sm[i];
+		atomicAdd(out, t);
+	}
+}
+
+void launch_update_diffnorm(long long n, const double *xtemp, double *x, double *d_out, cudaStream_t st)
+{
+	B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
+	if(n == 0) return;
+	const int grid = (int)std::max<long long>(1, std::min<long long>(DOT_BLOCKS, div_up(n, 256)));
+	update_diffnorm_kernel<<<grid,256,0,st>>>(n, xtemp, x, d_out);
+	B200_LAUNCHED();
+}
+
 void launch_vec_scal(long long n, double alpha, const double *in, double *out, cudaStream_t st)
 {
 	if(n == 0) return;

@@ -269,6 +269,8 @@ void launch_multi_dot(long long n, int nd, const double *const *a, const double 
 /// y += sum_l coef[l] * v[l]  for l < nv (coefficients read from device memory), nv <= 32 per call
 void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef,
                        double *y, cudaStream_t st, double sign = 1.0);
+/// x = xtemp, returning sum (xtemp - x)^2 in d_out[0] (Jacobi relaxation with tolerance checks)
+void launch_update_diffnorm(long long n, const double *xtemp, double *x, double *d_out, cudaStream_t st);
 /// out = alpha * in
 void launch_vec_scal(long long n, double alpha, const double *in, double *out, cudaStream_t st);
 
@@ -290,6 +292,10 @@ struct Prec {
 	DevBuf<double> hr, hz;              ///< staging for *_host entry points
 	bool computed = false;
 	int factor_sweeps_done = 0;         ///< sweeps used by the last compute (exact variants iterate)
+	// SolveParams of the reference (include/solverops_base.hpp:18-26), set by setApplyParams
+	double rtol = 0, atol = 0, dtol = 1e30;
+	bool ctol = false;
+	int maxits = 1;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double compute_ms = 0, apply_ms = 0;
 	// level-scheduled applies replayed as CUDA graphs (precond.cu::run_level_graph)

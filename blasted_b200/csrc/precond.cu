@@ -19,6 +19,7 @@
  * level-scheduled substitution.
  */
 #include "common.cuh"
+#include <cmath>
 
 namespace b200 {
 
@@ -405,10 +406,22 @@ void prec_apply_relax(Prec& P, const double *b, double *x, int maxits)
 		// solverops_jacobi.cpp:66-121,174-220 with ctol == false (what relax_local_blasted sets,
 		// blasted_petsc.cpp:532): xtemp = relax(x); x = xtemp
 		if(!P.xtemp.p) P.xtemp.alloc(n);
+		double refdiffnorm = 1;
 		for(int step = 0; step < maxits; step++) {
 			a.x = P.xtemp; a.xsrc = x;
 			launch_tri_sweep(A, TRI_RELAX, a, st);
-			B200_CUDA(cudaMemcpyAsync(x, P.xtemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
+			if(P.ctol) {
+				// tolerance checks of solverops_jacobi.cpp:86-105, 193-212
+				launch_update_diffnorm(n, P.xtemp, x, P.scratch, st);
+				double d2 = 0;
+				B200_CUDA(cudaMemcpyAsync(&d2, P.scratch.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+				B200_CUDA(cudaStreamSynchronize(st));
+				const double diffnorm = std::sqrt(d2);
+				if(step == 0) refdiffnorm = diffnorm;
+				if(diffnorm < P.atol || diffnorm/refdiffnorm < P.rtol || diffnorm/refdiffnorm > P.dtol)
+					break;
+			} else
+				B200_CUDA(cudaMemcpyAsync(x, P.xtemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 		}
 	}
 	else if(type == B200_GS) {

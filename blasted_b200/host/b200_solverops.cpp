@@ -71,6 +71,8 @@ void B200Preconditioner::apply(const double *const r, double *const __restrict z
 
 void B200Preconditioner::apply_relax(const double *const b, double *const __restrict x) const
 {
+	b200_prec_set_apply_params(dprec, solveparams.rtol, solveparams.atol, solveparams.dtol,
+	                           solveparams.ctol, solveparams.maxits);
 	check_runtime(b200_prec_apply_relax_host(dprec, b, x, solveparams.maxits));
 }
 

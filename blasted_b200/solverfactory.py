@@ -225,6 +225,8 @@ class Preconditioner:
         """SolveParams (include/solverops_base.hpp:18-26); only maxits is used with ctol=False,
         which is what the PETSc glue sets (src/blasted_petsc.cpp:532)."""
         self._maxits = int(maxits)
+        lib.b200_prec_set_apply_params(self._h, float(rtol), float(atol), float(dtol), int(ctol),
+                                       int(maxits))
 
     def compute(self) -> PrecInfo:
         info = np.zeros(6)

@@ -148,6 +148,12 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z);
 /** setApplyParams({.., maxits}) + apply_relax(b, x) (src/blasted_petsc.cpp:519-576): x is
  *  updated in place.  Fails with the reference's message where it throws
  *  ("ILU relaxation not implemented!", src/solverops_ilu0.cpp:215). */
+/** Preconditioner::setApplyParams(SolveParams{rtol, atol, dtol, ctol, maxits})
+ *  (include/solverops_base.hpp:18-26, :58).  With ctol != 0 the Jacobi relaxation stops on
+ *  ||x_new - x||_2 < atol, relative decrease < rtol or relative growth > dtol
+ *  (src/solverops_jacobi.cpp:86-105); the asynchronous relaxations never check (as the reference).
+ *  apply_relax with maxits <= 0 uses the maxits stored here. */
+int b200_prec_set_apply_params(b200_prec *p, double rtol, double atol, double dtol, int ctol, int maxits);
 int b200_prec_apply_relax(b200_prec *p, const double *d_b, double *d_x, int maxits);
 int b200_prec_apply_relax_host(b200_prec *p, const double *b, double *x, int maxits);
 int b200_prec_dim(const b200_prec *p);

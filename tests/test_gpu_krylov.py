@@ -96,3 +96,26 @@ def test_fgmres_matches_gcr(key, prec):
         its[name] = info.iters
         assert np.linalg.norm(b - orc().spmv(m, x))/np.linalg.norm(b) < 5e-10
     assert abs(its["fgmres"] - its["gcr"]) <= max(1, int(np.ceil(0.05*its["gcr"]))), its
+
+
+def test_runsolvetest_driver(tmp_path):
+    """The device counterpart of `runsolvetest` with the options of the reference's CTest entries
+    (tests/CMakeLists.txt:86-173, e.g. BSR4ILU0Colmajor / ThreadedBSR4ILU0Colmajor sweeps 10/15)."""
+    import scipy.io as sio
+    import scipy.sparse as sp
+    from blasted_b200 import testsolve
+    gm = golden_matrices()
+    m = case("2dcyl1_csr")
+    a = sp.csr_matrix((m.vals, m.bcolind, m.browptr), shape=(m.nbrows, m.nbrows))
+    sio.mmwrite(str(tmp_path/"a.mtx"), a, precision=17)
+    sio.mmwrite(str(tmp_path/"b.mtx"), gm["2dcyl1_b"].reshape(-1, 1), precision=17)
+    sio.mmwrite(str(tmp_path/"x.mtx"), gm["2dcyl1_x"].reshape(-1, 1), precision=17)
+    base = ["--mat_file", str(tmp_path/"a.mtx"), "--b_file", str(tmp_path/"b.mtx"),
+            "--x_file", str(tmp_path/"x.mtx"), "--solver_tol", "1e-10", "--test_tol", "1e-6"]
+    assert testsolve.main(base + ["--solver_type", "bcgs", "--preconditioner_type", "ilu0", "--mat_type",
+                                  "bsr", "--block_size", "4", "--build_sweeps", "10",
+                                  "--apply_sweeps", "15", "--apply_init_type", "init_jacobi"]) == 0
+    assert testsolve.main(base + ["--solver_type", "gcr", "--preconditioner_type", "level_sgs",
+                                  "--mat_type", "csr"]) == 0
+    assert testsolve.main(base + ["--solver_type", "fgmres", "--preconditioner_type", "seqilu0",
+                                  "--mat_type", "bsr", "--storage_order", "rowmajor"]) == 0

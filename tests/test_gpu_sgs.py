@@ -102,3 +102,28 @@ def test_noprec():
     p.apply_relax(r, x)
     assert np.array_equal(x, np.ones(m.dim))
     assert not p.relaxationAvailable() and p.dim() == m.dim
+
+
+def test_jacobi_relaxation_with_tolerance_checks():
+    """ctol = true path of JacobiSRPreconditioner::apply_relax (solverops_jacobi.cpp:86-105): stops
+    once the update is small relative to the first one."""
+    m = matgen.block_stencil((12, 12), 4, SEED)
+    p = make(m, "jacobi")
+    p.compute()
+    rng = np.random.default_rng(SEED)
+    b = orc().spmv(m, rng.standard_normal(m.dim))
+    d = orc().jacobi_setup(m)
+    # emulate the reference loop on the host with the oracle's single relaxation step
+    x = np.zeros(m.dim)
+    ref0 = None
+    for step in range(200):
+        xn = orc().jacobi_relax(m, d, 1, b, x)
+        diff = np.linalg.norm(xn - x)
+        x = xn
+        ref0 = diff if step == 0 else ref0
+        if diff < 1e-50 or diff/ref0 < 1e-6 or diff/ref0 > 1e10:
+            break
+    p.setApplyParams(rtol=1e-6, atol=1e-50, dtol=1e10, ctol=True, maxits=200)
+    xg = p.apply_relax(b, np.zeros(m.dim))
+    assert relerr(xg, x) < 1e-11
+    assert step < 199
