@@ -33,6 +33,9 @@ def timeit(fn, reps=9, warm=3):
 
 
 def row(name, ms, nbytes):
+    if ms <= 0:
+        print(f"| {name} | - | - | - | - |")
+        return
     gbs = nbytes/ms/1e6
     print(f"| {name} | {ms:.3f} | {nbytes/1e9:.3f} | {gbs:.0f} | {gbs/PEAK:.2f} |")
 
