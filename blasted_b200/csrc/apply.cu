@@ -98,7 +98,7 @@ tri_scalar_kernel(const TriDev a)
 }
 
 template <int BS, int KIND, bool VEC>
-__global__ void __launch_bounds__(256, (BS <= 4 ? 6 : 4))
+__global__ void __launch_bounds__(256, 6)
 tri_block_kernel(const TriDev a)
 {
 	constexpr int GPW = 32/BS;
