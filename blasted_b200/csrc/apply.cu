@@ -154,11 +154,128 @@ tri_block_kernel(const TriDev a)
 	if(valid) a.x[(size_t)row*BS + r] = out;
 }
 
+/// Persistent, software-pipelined form of tri_block_kernel for the plain asynchronous sweeps (whole
+/// row range, no level list).  A row's loads form a chain  row indices -> column indices -> x_j;
+/// with two or three blocks per part the chain, not the bandwidth, bounds the one-shot kernel.
+/// Here every group walks rows t, t+G, t+2G, ... and keeps the indices of its row after next and the
+/// column indices of its next row in registers, so that in the steady state every load of the
+/// current row - block rows, vector segments, right-hand side, diagonal block - has a known
+/// address and is requested at once.  Arithmetic and the single final store per row are those of
+/// tri_block_kernel; rows are still visited in ascending (descending) waves.
+template <int BS, int KIND, bool VEC>
+__global__ void __launch_bounds__(256, 4)
+tri_block_pipe_kernel(const TriDev a)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	constexpr int K = 3;                       // column indices prefetched per row part
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const int wpc = blockDim.x >> 5;
+	const long long stride = (long long)gridDim.x*wpc*GPW;
+	const long long wbase = ((long long)blockIdx.x*wpc + (threadIdx.x >> 5))*GPW;
+	const int nrows = a.row_end - a.row_begin;
+
+	auto load_meta = [&](const long long t, int& js, int& je, int& d) {
+		js = 0; je = 0; d = -1;
+		if(g < GPW && t < nrows) {
+			const int row = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
+			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+			d = __ldg(a.diagind + row);
+			part_range<KIND>(s, d, e, js, je);
+		}
+	};
+	auto load_cols = [&](const int js, const int je, int (&c)[K]) {
+#pragma unroll
+		for(int q = 0; q < K; q++) c[q] = (js + q < je) ? __ldg(a.bcolind + js + q) : 0;
+	};
+
+	int js1, je1, d1, c1[K], js2, je2, d2;
+	load_meta(wbase + g, js1, je1, d1);
+	load_cols(js1, je1, c1);
+	load_meta(wbase + g + stride, js2, je2, d2);
+
+	for(long long tw = wbase; tw < nrows; tw += stride) {
+		const long long t = tw + g;
+		const int js = js1, je = je1, d = d1;
+		int cols[K];
+#pragma unroll
+		for(int q = 0; q < K; q++) cols[q] = c1[q];
+		js1 = js2; je1 = je2; d1 = d2;
+		load_cols(js1, je1, c1);
+		load_meta(t + 2*stride, js2, je2, d2);
+
+		const bool valid = (g < GPW) && (t < nrows);
+		const int row = valid ? (a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t) : 0;
+		double acc = 0, rhs = 0;
+		double dr[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) dr[c] = 0;
+		if(valid) {
+			rhs = __ldg(a.rhs + (size_t)row*BS + r);
+			if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
+			if(KIND != TRI_ILU_LOWER)
+				BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
+#pragma unroll
+			for(int q = 0; q < K; q++) {
+				const int jj = js + q;
+				if(jj < je && !(KIND == TRI_RELAX && jj == d)) {
+					double av[BS], xv[BS];
+					BlkIO<BS>::template load_row<false>(a.vals + (size_t)jj*BS2, r, av);
+					load_seg<BS,true,VEC>(a.xsrc + (size_t)cols[q]*BS, xv);
+#pragma unroll
+					for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+				}
+			}
+			for(int jj = js + K; jj < je; jj++) {
+				if(KIND == TRI_RELAX && jj == d) continue;
+				const int col = __ldg(a.bcolind + jj);
+				double av[BS], xv[BS];
+				BlkIO<BS>::template load_row<false>(a.vals + (size_t)jj*BS2, r, av);
+				load_seg<BS,true,VEC>(a.xsrc + (size_t)col*BS, xv);
+#pragma unroll
+				for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+			}
+		}
+		double out;
+		if(KIND == TRI_ILU_LOWER) out = rhs - acc;
+		else {
+			const double tv = (KIND == TRI_SGS_BWD) ? acc : rhs - acc;
+			double prod = 0;
+#pragma unroll
+			for(int c = 0; c < BS; c++) {
+				const double tc = __shfl_sync(0xffffffffu, tv, min(g*BS + c, 31));
+				prod = fma(dr[c], tc, prod);
+			}
+			out = (KIND == TRI_SGS_BWD) ? rhs - prod : prod;
+		}
+		if(valid) a.x[(size_t)row*BS + r] = out;
+	}
+}
+
+/// Resident CTAs of a persistent kernel over all SMs (cached per kernel), capped by the work
+template <typename Kern>
+static int resident_grid(Kern kernel, long long rows_per_cta, long long nrows)
+{
+	static int cached = 0;
+	if(!cached) {
+		int dev = 0, sms = 148, per = 4;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 256, 0) != cudaSuccess || per < 1)
+			per = 4;
+		cached = sms*per;
+	}
+	const long long need = (nrows + rows_per_cta - 1)/rows_per_cta;
+	return (int)std::max<long long>(1, std::min<long long>(cached, need));
+}
+
 template <int KIND>
 static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cudaStream_t st)
 {
 	const long long nrows = d.row_end - d.row_begin;
 	if(nrows <= 0) return;
+	static const bool one_shot = getenv("B200_TRI1") != nullptr;      // A/B switch (development)
 	if(A.bs == 1) {
 #define B200_TRI_CASE(L)                                                           \
 		{                                                                          \
@@ -172,6 +289,12 @@ static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cu
 		else B200_TRI_CASE(32)
 #undef B200_TRI_CASE
 	}
+	else if(A.bs == 4 && !d.rows && aligned32(d.xsrc) && !one_shot) {
+		auto k = tri_block_pipe_kernel<4,KIND,true>;
+		k<<<resident_grid(k, 64, nrows), 256, 0, st>>>(d);
+	}
+	// (bs = 5 measured slower pipelined - 64 registers cost more occupancy than the chain costs
+	// time with 3-block parts - and stays on the one-shot kernel.)
 	else if(A.bs == 4) {
 		const long long nwarps = (nrows + 7)/8;
 		if(aligned32(d.xsrc))
