@@ -48,6 +48,12 @@ SYMBOLS = {
     "b200_mat_nbrows": (_i, [_vp]),
     "b200_mat_nnzb": (_ll, [_vp]),
     "b200_mat_set_stream": (_i, [_vp, _vp]),
+    "b200_mat_create_coo": (_i, [_i, _ll, _vp, _vp, _vp, _i, _i, _i, _pp]),
+    "b200_mat_get_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200_mat_reorder": (_i, [_vp, _vp, _vp, _i, _i]),
+    "b200_mat_scale": (_i, [_vp, _vp, _vp, _i, _i]),
+    "b200_vec_reorder": (_i, [_vp, _ll, _i, _vp, _i, _i]),
+    "b200_vec_scale": (_i, [_vp, _ll, _i, _vp, _i, _i]),
     "b200_mat_apply": (_i, [_vp, _vp, _vp]),
     "b200_mat_apply_host": (_i, [_vp, _vp, _vp]),
     "b200_mat_gemv3": (_i, [_vp, _d, _vp, _d, _vp, _vp]),

@@ -64,7 +64,7 @@ static void require_device()
 	}
 }
 
-static void finish_matrix(Mat& A, const int *h_diagind, cudaStream_t st)
+void finish_matrix(Mat& A, const int *h_diagind, cudaStream_t st)
 {
 	// row statistics for kernel selection
 	A.avg_row_len = A.nbrows ? (double)A.nnzb/A.nbrows : 0.0;
@@ -156,6 +156,22 @@ struct LocalOps : public KrylovOps {
 		return dout.p;
 	}
 };
+
+namespace {
+/// device copy of a host array, or the caller's device pointer itself
+template <typename T>
+struct Staged {
+	DevBuf<T> buf;
+	const T *p = nullptr;
+	Staged(const T *src, size_t n, bool on_device, cudaStream_t st) {
+		if(!src) return;
+		if(on_device) { p = src; return; }
+		buf.alloc(std::max<size_t>(n, 1));
+		if(n) B200_CUDA(cudaMemcpyAsync(buf.p, src, n*sizeof(T), cudaMemcpyHostToDevice, st));
+		p = buf.p;
+	}
+};
+}
 
 }  // namespace b200
 
@@ -254,6 +270,109 @@ int b200_mat_dim(const b200_mat *m) { return m->m.dim(); }
 int b200_mat_nbrows(const b200_mat *m) { return m->m.nbrows; }
 long long b200_mat_nnzb(const b200_mat *m) { return m->m.nnzb; }
 int b200_mat_set_stream(b200_mat *m, void *s) { m->m.stream = (cudaStream_t)s; return 0; }
+
+// ---- front end (frontend.cu): coordinate input, permutation, scaling
+
+
+int b200_mat_create_coo(int nrows, long long nnz, const int *rowind, const int *colind,
+                        const double *vals, int bs, int blockstorage, int on_device, b200_mat **out)
+{
+	return guarded([&] {
+		require_device();
+		if(!out) throw Error("null output handle");
+		*out = nullptr;
+		if(!(bs == 1 || bs == 3 || bs == 4 || bs == 5 || bs == 7))
+			throw Error("Block size " + std::to_string(bs) + " not supported");
+		if(blockstorage != B200_COLMAJOR && blockstorage != B200_ROWMAJOR)
+			throw Error("Block ordering must be either rowmajor or colmajor!");
+		if(nnz > 0 && (!rowind || !colind || !vals)) throw Error("null coordinate arrays");
+		b200_mat *h = new b200_mat;
+		try {
+			Mat& A = h->m;
+			A.bs = bs; A.blockstorage = blockstorage;
+			cudaStream_t st = A.stream;
+			Staged<int> r(rowind, nnz, on_device != 0, st), c(colind, nnz, on_device != 0, st);
+			Staged<double> v(vals, nnz, on_device != 0, st);
+			coo_to_mat(A, nrows, nnz, r.p, c.p, v.p, st);
+		} catch(...) { delete h; throw; }
+		*out = h;
+	});
+}
+
+int b200_mat_get_host(const b200_mat *m, int *browptr, int *bcolind, int *diagind, double *vals)
+{
+	return guarded([&] {
+		const Mat& A = m->m;
+		cudaStream_t st = A.stream;
+		if(browptr) B200_CUDA(cudaMemcpyAsync(browptr, A.browptr.p, ((size_t)A.nbrows+1)*sizeof(int), cudaMemcpyDeviceToHost, st));
+		if(bcolind && A.nnzb) B200_CUDA(cudaMemcpyAsync(bcolind, A.bcolind.p, A.nnzb*sizeof(int), cudaMemcpyDeviceToHost, st));
+		if(diagind && A.nbrows) B200_CUDA(cudaMemcpyAsync(diagind, A.diagind.p, A.nbrows*sizeof(int), cudaMemcpyDeviceToHost, st));
+		if(vals && A.nnzb) {
+			const size_t n = (size_t)A.nnzb*A.bs*A.bs;
+			if(A.bs > 1 && (A.blockstorage == B200_ROWMAJOR) != device_rowmajor(A.bs)) {
+				DevBuf<double> t;
+				t.alloc(n);
+				transpose_blocks(A.bs, A.nnzb, A.vals, t, st);
+				B200_CUDA(cudaMemcpyAsync(vals, t.p, n*sizeof(double), cudaMemcpyDeviceToHost, st));
+				B200_CUDA(cudaStreamSynchronize(st));
+			} else
+				B200_CUDA(cudaMemcpyAsync(vals, A.vals.p, n*sizeof(double), cudaMemcpyDeviceToHost, st));
+		}
+		B200_CUDA(cudaStreamSynchronize(st));
+	});
+}
+
+int b200_mat_reorder(b200_mat *m, const int *rord, const int *cord, int inverse, int on_device)
+{
+	return guarded([&] {
+		Mat& A = m->m;
+		Staged<int> r(rord, A.nbrows, on_device != 0, A.stream), c(cord, A.nbrows, on_device != 0, A.stream);
+		mat_reorder(A, r.p, c.p, inverse != 0, A.stream);
+	});
+}
+
+int b200_mat_scale(b200_mat *m, const double *rowscale, const double *colscale, int inverse,
+                   int on_device)
+{
+	return guarded([&] {
+		Mat& A = m->m;
+		Staged<double> r(rowscale, A.nbrows, on_device != 0, A.stream), c(colscale, A.nbrows, on_device != 0, A.stream);
+		mat_scale(A, r.p, c.p, inverse != 0, A.stream);
+		B200_CUDA(cudaStreamSynchronize(A.stream));
+	});
+}
+
+int b200_vec_reorder(double *vec, long long n, int bs, const int *ord, int inverse, int on_device)
+{
+	return guarded([&] {
+		require_device();
+		if(n < 0 || bs < 1) throw Error("invalid vector size");
+		if(!ord || n == 0) return;                  // no ordering set: nothing to do (:222-225)
+		if(on_device) { vec_reorder(n, bs, ord, inverse != 0, vec, 0); return; }
+		Staged<int> o(ord, n, false, 0);
+		DevBuf<double> v;
+		v.alloc((size_t)n*bs);
+		B200_CUDA(cudaMemcpyAsync(v.p, vec, (size_t)n*bs*sizeof(double), cudaMemcpyHostToDevice, 0));
+		vec_reorder(n, bs, o.p, inverse != 0, v, 0);
+		B200_CUDA(cudaMemcpy(vec, v.p, (size_t)n*bs*sizeof(double), cudaMemcpyDeviceToHost));
+	});
+}
+
+int b200_vec_scale(double *vec, long long n, int bs, const double *scale, int inverse, int on_device)
+{
+	return guarded([&] {
+		require_device();
+		if(n < 0 || bs < 1) throw Error("invalid vector size");
+		if(!scale || n == 0) return;
+		if(on_device) { vec_scale(n, bs, scale, inverse != 0, vec, 0); B200_CUDA(cudaStreamSynchronize(0)); return; }
+		Staged<double> sc(scale, n, false, 0);
+		DevBuf<double> v;
+		v.alloc((size_t)n*bs);
+		B200_CUDA(cudaMemcpyAsync(v.p, vec, (size_t)n*bs*sizeof(double), cudaMemcpyHostToDevice, 0));
+		vec_scale(n, bs, sc.p, inverse != 0, v, 0);
+		B200_CUDA(cudaMemcpy(vec, v.p, (size_t)n*bs*sizeof(double), cudaMemcpyDeviceToHost));
+	});
+}
 
 int b200_mat_apply(const b200_mat *m, const double *d_x, double *d_y)
 {

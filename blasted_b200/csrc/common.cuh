@@ -134,6 +134,16 @@ void build_browind(const Mat& A, cudaStream_t st);
 /// locate diagonals; returns number of rows without one
 int find_diagonals(Mat& A, cudaStream_t st);
 int max_row_length(const Mat& A, cudaStream_t st);
+/// derived arrays of a matrix whose browptr/bcolind are set: browind, diagind, row statistics (api.cu)
+void finish_matrix(Mat& A, const int *h_diagind, cudaStream_t st);
+
+// frontend.cu: coordinate triplets -> CSR/BSR, permutation and scaling of a resident matrix
+void coo_to_mat(Mat& A, int nrows, long long nnz, const int *d_row, const int *d_col,
+                const double *d_val, cudaStream_t st);
+void mat_reorder(Mat& A, const int *d_rord, const int *d_cord, bool inverse, cudaStream_t st);
+void vec_reorder(long long n, int bs, const int *d_ord, bool inverse, double *d_vec, cudaStream_t st);
+void mat_scale(Mat& A, const double *d_rowscale, const double *d_colscale, bool inverse, cudaStream_t st);
+void vec_scale(long long n, int bs, const double *d_scale, bool inverse, double *d_vec, cudaStream_t st);
 
 // pattern.cu
 struct IluPattern {

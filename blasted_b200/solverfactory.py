@@ -134,6 +134,31 @@ class SRMatrixView:
                                        m.bcolind.ctypes.data_as(C.c_void_p),
                                        m.vals.ctypes.data_as(C.c_void_p), di, C.byref(self._h)))
 
+    @classmethod
+    def from_handle(cls, handle, bs: int, rowmajor: bool) -> "SRMatrixView":
+        """Wraps a matrix that was built on the device (front end); the host copy is fetched."""
+        self = cls.__new__(cls)
+        self._h = handle
+        self._bs, self._rowmajor = bs, rowmajor
+        self.m = None
+        self.m = self.to_host()
+        return self
+
+    def to_host(self) -> SRMatrix:
+        """The resident matrix as host arrays in the reference's raw layout."""
+        bs = self.m.bs if self.m is not None else self._bs
+        rowmajor = self.m.rowmajor if self.m is not None else self._rowmajor
+        nb, nnzb = lib.b200_mat_nbrows(self._h), lib.b200_mat_nnzb(self._h)
+        browptr = np.zeros(nb + 1, dtype=np.int32)
+        bcolind = np.zeros(nnzb, dtype=np.int32)
+        diagind = np.zeros(nb, dtype=np.int32)
+        vals = np.zeros(nnzb * bs * bs, dtype=np.float64)
+        check(lib.b200_mat_get_host(self._h, browptr.ctypes.data_as(C.c_void_p),
+                                    bcolind.ctypes.data_as(C.c_void_p),
+                                    diagind.ctypes.data_as(C.c_void_p),
+                                    vals.ctypes.data_as(C.c_void_p)))
+        return SRMatrix(nb, bs, browptr, bcolind, vals, diagind, rowmajor)
+
     def dim(self) -> int:
         return lib.b200_mat_dim(self._h)
 

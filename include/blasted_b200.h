@@ -120,6 +120,35 @@ int b200_mat_nbrows(const b200_mat *m);
 long long b200_mat_nnzb(const b200_mat *m);
 int b200_mat_set_stream(b200_mat *m, void *cuda_stream);
 
+/* ---- front end: the step before the path.  Every array argument is
+ *      a host pointer when on_device == 0 and a device pointer otherwise. ---- */
+
+/** Coordinate triplets (0-based, any order, square matrix of `nrows` scalar rows) to a resident
+ *  CSR (bs = 1) or BSR matrix with sorted columns, located diagonals and zero-filled blocks.
+ *  Replaces COOMatrix's row/column sort and convertToCSR / convertToBSR<bs,stor>
+ *  (src/coomatrix.cpp:222-403); `blockstorage` is the layout b200_mat_get_host hands back. */
+int b200_mat_create_coo(int nrows, long long nnz, const int *rowind, const int *colind,
+                        const double *vals, int bs, int blockstorage, int on_device, b200_mat **out);
+/** Copies the matrix back to host arrays (any may be NULL): browptr[nbrows+1], bcolind[nnzb],
+ *  diagind[nbrows], vals[nnzb*bs*bs] in the caller's block layout. */
+int b200_mat_get_host(const b200_mat *m, int *browptr, int *bcolind, int *diagind, double *vals);
+/** Reordering::applyOrdering on the resident matrix (src/reorderingscaling.cpp:77-205):
+ *  forward - new row i is old row rord[i], columns renamed by the inverse of cord and re-sorted;
+ *  inverse - old row i moves to row rord[i], columns renamed by cord.  Either may be NULL.
+ *  diagind is located again afterwards (the reference leaves it stale).  Preconditioners built on
+ *  the matrix before the call must be rebuilt. */
+int b200_mat_reorder(b200_mat *m, const int *rord, const int *cord, int inverse, int on_device);
+/** ReorderingScaling::applyScaling on the resident matrix (src/reorderingscaling.cpp:282-337):
+ *  block row i times (inverse: divided by) rowscale[i], then block column j by colscale[j]. */
+int b200_mat_scale(b200_mat *m, const double *rowscale, const double *colscale, int inverse,
+                   int on_device);
+/** Reordering::applyOrdering on a vector of n blocks of bs (src/reorderingscaling.cpp:211-266):
+ *  forward vec[i] <- vec[ord[i]], inverse vec[ord[i]] <- vec[i]; ord is the row or the column
+ *  ordering according to the direction wanted.  ord == NULL is a no-op. */
+int b200_vec_reorder(double *vec, long long n, int bs, const int *ord, int inverse, int on_device);
+/** ReorderingScaling::applyScaling on a vector (src/reorderingscaling.cpp:340-368). */
+int b200_vec_scale(double *vec, long long n, int bs, const double *scale, int inverse, int on_device);
+
 /** y = A x  : AbstractLinearOperator::apply (include/linearoperator.hpp:36),
  *  BLAS_CSR/BLAS_BSR::matrix_apply (src/blas/matvecs.cpp:25-48, 78-91). */
 int b200_mat_apply(const b200_mat *m, const double *d_x, double *d_y);

@@ -81,6 +81,57 @@ class _Oracle:
         L.orc_jacobi_relax.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _dp, C.c_int,
                                        _dp, _dp, _dp]
         L.orc_diagonal_dominance.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp]
+        L.orc_coo_convert.restype = C.c_longlong
+        L.orc_coo_convert.argtypes = [C.c_int, C.c_longlong, _ip, _ip, _dp, C.c_int, C.c_int, vp, vp,
+                                      vp, vp]
+        L.orc_reorder_matrix.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, vp, vp, C.c_int]
+        L.orc_reorder_vector.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp]
+        L.orc_scale_matrix.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, vp, vp, C.c_int]
+        L.orc_scale_vector.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp]
+
+    # ---- front end ----
+    def coo_convert(self, nrows, rowind, colind, values, bs, rowmajor=False):
+        """-> (browptr, bcolind, diagind, vals) as COOMatrix sort + convertToCSR/BSR produce them"""
+        r = np.ascontiguousarray(rowind, dtype=np.int32)
+        c = np.ascontiguousarray(colind, dtype=np.int32)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        nnzb = self.lib.orc_coo_convert(nrows, len(v), r, c, v, bs, int(rowmajor), None, None, None, None)
+        nb = nrows // bs
+        browptr = np.zeros(nb + 1, dtype=np.int32)
+        bcolind = np.zeros(max(nnzb, 1), dtype=np.int32)
+        diagind = np.zeros(max(nb, 1), dtype=np.int32)
+        vals = np.zeros(max(nnzb * bs * bs, 1))
+        self.lib.orc_coo_convert(nrows, len(v), r, c, v, bs, int(rowmajor), _opt(browptr),
+                                 _opt(bcolind), _opt(diagind), _opt(vals))
+        return browptr, bcolind[:nnzb], diagind[:nb], vals[:nnzb * bs * bs]
+
+    def reorder_matrix(self, m, rord, cord, inverse=False):
+        """-> (browptr, bcolind, vals) of the permuted matrix (copies)"""
+        bp, bc, v = m.browptr.copy(), m.bcolind.copy(), m.vals.copy()
+        ro = None if rord is None else np.ascontiguousarray(rord, dtype=np.int32)
+        co = None if cord is None else np.ascontiguousarray(cord, dtype=np.int32)
+        self.lib.orc_reorder_matrix(m.bs, m.nbrows, bp, bc, v, _opt(ro), _opt(co), int(inverse))
+        return bp, bc, v
+
+    def reorder_vector(self, bs, ordering, vec, inverse=False):
+        o = np.ascontiguousarray(ordering, dtype=np.int32)
+        out = np.array(vec, dtype=np.float64)
+        self.lib.orc_reorder_vector(bs, len(o), o, int(inverse), out)
+        return out
+
+    def scale_matrix(self, m, rowscale, colscale, inverse=False):
+        v = m.vals.copy()
+        rs = None if rowscale is None else np.ascontiguousarray(rowscale, dtype=np.float64)
+        cs = None if colscale is None else np.ascontiguousarray(colscale, dtype=np.float64)
+        self.lib.orc_scale_matrix(m.bs, m.nbrows, m.browptr, m.bcolind, v, _opt(rs), _opt(cs),
+                                  int(inverse))
+        return v
+
+    def scale_vector(self, bs, scale, vec, inverse=False):
+        sc = np.ascontiguousarray(scale, dtype=np.float64)
+        out = np.array(vec, dtype=np.float64)
+        self.lib.orc_scale_vector(bs, len(sc), sc, int(inverse), out)
+        return out
 
     # ---- matrix ops ----
     def spmv(self, m, x):
@@ -349,6 +400,44 @@ class _Ref:
                                 _dp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int),
                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_num_threads.argtypes = [C.c_int]
+        L.ref_read_mtx.restype = vp
+        L.ref_read_mtx.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        L.ref_srmat_nbrows.argtypes = [vp]
+        L.ref_srmat_nnzb.argtypes = [vp]
+        L.ref_srmat_copy.argtypes = [vp, _ip, _ip, _ip, _dp]
+        L.ref_srmat_destroy.argtypes = [vp]
+        L.ref_reorder_scale.argtypes = [C.c_int, C.c_int] + [vp] * 8 + [C.c_int, vp, vp]
+
+    # ---- front end ----
+    def read_mtx(self, path, bs, rowmajor=False):
+        """COOMatrix::readMatrixMarket + getSRMatrixFromCOO -> (browptr, bcolind, diagind, vals)"""
+        h = self.lib.ref_read_mtx(str(path).encode(), bs, int(rowmajor))
+        if not h:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        nb, nnzb = self.lib.ref_srmat_nbrows(h), self.lib.ref_srmat_nnzb(h)
+        browptr = np.zeros(nb + 1, dtype=np.int32)
+        bcolind = np.zeros(max(nnzb, 1), dtype=np.int32)
+        diagind = np.zeros(max(nb, 1), dtype=np.int32)
+        vals = np.zeros(max(nnzb * bs * bs, 1))
+        self.lib.ref_srmat_copy(h, browptr, bcolind, diagind, vals)
+        self.lib.ref_srmat_destroy(h)
+        return browptr, bcolind[:nnzb], diagind[:nb], vals[:nnzb * bs * bs]
+
+    def reorder_scale(self, m, rord=None, cord=None, rowscale=None, colscale=None, inverse=False,
+                      rowvec=None, colvec=None):
+        """Reordering / ReorderingScaling applied to copies -> (browptr, bcolind, vals, rowvec, colvec)"""
+        def ia(a):
+            return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+        def da(a):
+            return None if a is None else np.array(a, dtype=np.float64)
+        bp, bc, v, di = m.browptr.copy(), m.bcolind.copy(), m.vals.copy(), m.diagind.copy()
+        ro, co, rs, cs, rv, cv = ia(rord), ia(cord), da(rowscale), da(colscale), da(rowvec), da(colvec)
+        rc = self.lib.ref_reorder_scale(m.bs, m.nbrows, _opt(bp), _opt(bc), _opt(v), _opt(di), _opt(ro),
+                                        _opt(co), _opt(rs), _opt(cs), int(inverse), _opt(rv), _opt(cv))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return bp, bc, v, rv, cv
 
     def num_threads(self):
         return self.lib.ref_num_threads()

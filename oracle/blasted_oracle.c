@@ -674,3 +674,206 @@ void orc_diagonal_dominance(int bs, int rm, int nbrows, const int *browptr, cons
 	out[2] = uddavg/((double)nbrows*bs);
 	out[3] = uddmin;
 }
+
+/* ---------- front end ---------- */
+
+typedef struct { int r, c; double v; long long k; } orc_entry;
+
+static int cmp_entry(const void *a, const void *b)
+{
+	const orc_entry *x = (const orc_entry*)a, *y = (const orc_entry*)b;
+	if(x->r != y->r) return x->r < y->r ? -1 : 1;
+	if(x->c != y->c) return x->c < y->c ? -1 : 1;
+	return x->k < y->k ? -1 : (x->k > y->k);            /* input order among duplicates */
+}
+
+/* src/coomatrix.cpp:222-403 */
+long long orc_coo_convert(int nrows, long long nnz, const int *rowind, const int *colind,
+                          const double *val, int bs, int rm, int *browptr, int *bcolind,
+                          int *diagind, double *vals)
+{
+	orc_entry *e = (orc_entry*)malloc((size_t)(nnz > 0 ? nnz : 1)*sizeof(orc_entry));
+	for(long long i = 0; i < nnz; i++) { e[i].r = rowind[i]; e[i].c = colind[i]; e[i].v = val[i]; e[i].k = i; }
+	qsort(e, (size_t)nnz, sizeof(orc_entry), cmp_entry);
+	int *rowptr = (int*)calloc((size_t)nrows + 1, sizeof(int));
+	for(long long i = 0; i < nnz; i++) rowptr[e[i].r + 1]++;
+	for(int i = 0; i < nrows; i++) rowptr[i+1] += rowptr[i];
+
+	long long bnnz = 0;
+	if(bs == 1) {
+		/* convertToCSR :262-297 */
+		bnnz = nnz;
+		if(bcolind) {
+			for(int i = 0; i <= nrows; i++) browptr[i] = rowptr[i];
+			for(int i = 0; i < nrows; i++) diagind[i] = -1;
+			for(long long j = 0; j < nnz; j++) {
+				bcolind[j] = e[j].c; vals[j] = e[j].v;
+				if(e[j].c == e[j].r) diagind[e[j].r] = (int)j;
+			}
+		}
+	} else {
+		/* convertToBSR :299-403 */
+		const int nbrows = nrows/bs, bs2 = bs*bs;
+		int *bptr = (int*)calloc((size_t)nbrows + 1, sizeof(int));
+		int *bcol = (int*)malloc((size_t)(nnz > 0 ? nnz : 1)*sizeof(int));
+		int *bdiag = (int*)malloc((size_t)(nbrows > 0 ? nbrows : 1)*sizeof(int));
+		char *tally = (char*)calloc((size_t)nbrows + 1, 1);
+		for(int i = 0; i < nbrows; i++) bdiag[i] = -1;
+		for(int irow = 0; irow < nrows; irow++) {
+			const int brow = irow/bs;
+			for(int j = rowptr[irow]; j < rowptr[irow+1]; j++) {
+				const int bc = e[j].c/bs;
+				if(!tally[brow]) { bptr[brow] = (int)bnnz; tally[brow] = 1; }
+				long long it = bptr[brow];
+				while(it < bnnz && bcol[it] != bc) it++;
+				if(it == bnnz) {
+					bcol[bnnz] = bc;
+					if(bc == brow) bdiag[brow] = (int)bnnz;
+					bnnz++;
+				}
+			}
+		}
+		bptr[nbrows] = (int)bnnz;
+		for(int i = nbrows-1; i > 0; i--)
+			if(bptr[i] == 0) bptr[i] = bptr[i+1];
+		if(bcolind) {
+			for(int i = 0; i <= nbrows; i++) browptr[i] = bptr[i];
+			for(int i = 0; i < nbrows; i++) diagind[i] = bdiag[i];
+			for(long long i = 0; i < bnnz; i++) bcolind[i] = bcol[i];
+			for(long long i = 0; i < bnnz*bs2; i++) vals[i] = 0;
+			for(int irow = 0; irow < nrows; irow++) {
+				const int brow = irow/bs;
+				for(int j = rowptr[irow]; j < rowptr[irow+1]; j++) {
+					const int c = e[j].c, bc = c/bs;
+					const int off = rm ? (irow - brow*bs)*bs + c - bc*bs : (c - bc*bs)*bs + irow - brow*bs;
+					int p = bptr[brow];
+					while(p < bptr[brow+1] && bcol[p] != bc) p++;
+					vals[(size_t)p*bs2 + off] = e[j].v;
+				}
+			}
+		}
+		free(bptr); free(bcol); free(bdiag); free(tally);
+	}
+	free(e); free(rowptr);
+	return bnnz;
+}
+
+/* internal::sortBlockInnerDimension (src/helper_algorithms.hpp): sort a row's blocks by column */
+static void sort_row_blocks(int bs2, int n, int *col, double *v)
+{
+	double *tmp = (double*)malloc((size_t)bs2*sizeof(double));
+	for(int i = 1; i < n; i++) {
+		const int c = col[i];
+		memcpy(tmp, v + (size_t)i*bs2, (size_t)bs2*sizeof(double));
+		int j = i - 1;
+		while(j >= 0 && col[j] > c) {
+			col[j+1] = col[j];
+			memcpy(v + (size_t)(j+1)*bs2, v + (size_t)j*bs2, (size_t)bs2*sizeof(double));
+			j--;
+		}
+		col[j+1] = c;
+		memcpy(v + (size_t)(j+1)*bs2, tmp, (size_t)bs2*sizeof(double));
+	}
+	free(tmp);
+}
+
+/* src/reorderingscaling.cpp:77-205 */
+void orc_reorder_matrix(int bs, int nbrows, int *browptr, int *bcolind, double *vals,
+                        const int *rord, const int *cord, int inverse)
+{
+	const int bs2 = bs*bs;
+	const int nnzb = browptr[nbrows];
+	if(rord) {
+		int *tptr = (int*)malloc(((size_t)nbrows + 1)*sizeof(int));
+		int *tcol = (int*)malloc((size_t)(nnzb > 0 ? nnzb : 1)*sizeof(int));
+		double *tval = (double*)malloc((size_t)(nnzb > 0 ? nnzb : 1)*bs2*sizeof(double));
+		if(!inverse) {
+			/* new row i is old row rord[i] (:83-115) */
+			int pos = 0;
+			for(int i = 0; i < nbrows; i++) {
+				tptr[i] = pos;
+				for(int jj = browptr[rord[i]]; jj < browptr[rord[i]+1]; jj++, pos++) {
+					tcol[pos] = bcolind[jj];
+					memcpy(tval + (size_t)pos*bs2, vals + (size_t)jj*bs2, (size_t)bs2*sizeof(double));
+				}
+			}
+			tptr[nbrows] = pos;
+		} else {
+			/* old row i moves to row rord[i] (:144-178) */
+			int *len = (int*)calloc((size_t)nbrows + 1, sizeof(int));
+			for(int i = 0; i < nbrows; i++) len[rord[i]] = browptr[i+1] - browptr[i];
+			tptr[0] = 0;
+			for(int i = 0; i < nbrows; i++) tptr[i+1] = tptr[i] + len[i];
+			for(int i = 0; i < nbrows; i++) {
+				int pos = tptr[rord[i]];
+				for(int jj = browptr[i]; jj < browptr[i+1]; jj++, pos++) {
+					tcol[pos] = bcolind[jj];
+					memcpy(tval + (size_t)pos*bs2, vals + (size_t)jj*bs2, (size_t)bs2*sizeof(double));
+				}
+			}
+			free(len);
+		}
+		memcpy(browptr, tptr, ((size_t)nbrows + 1)*sizeof(int));
+		memcpy(bcolind, tcol, (size_t)nnzb*sizeof(int));
+		memcpy(vals, tval, (size_t)nnzb*bs2*sizeof(double));
+		free(tptr); free(tcol); free(tval);
+	}
+	if(cord) {
+		/* forward renames with the inverse permutation, inverse with cord itself (:117-139,181-203) */
+		int *map = (int*)malloc((size_t)(nbrows > 0 ? nbrows : 1)*sizeof(int));
+		if(!inverse) for(int i = 0; i < nbrows; i++) map[cord[i]] = i;
+		else for(int i = 0; i < nbrows; i++) map[i] = cord[i];
+		for(int i = 0; i < nbrows; i++) {
+			for(int jj = browptr[i]; jj < browptr[i+1]; jj++) bcolind[jj] = map[bcolind[jj]];
+			sort_row_blocks(bs2, browptr[i+1] - browptr[i], bcolind + browptr[i],
+			                vals + (size_t)browptr[i]*bs2);
+		}
+		free(map);
+	}
+}
+
+/* src/reorderingscaling.cpp:211-266 */
+void orc_reorder_vector(int bs, int n, const int *ord, int inverse, double *vec)
+{
+	if(!ord || n <= 0) return;
+	double *tv = (double*)malloc((size_t)n*bs*sizeof(double));
+	memcpy(tv, vec, (size_t)n*bs*sizeof(double));
+	for(int i = 0; i < n; i++)
+		for(int k = 0; k < bs; k++) {
+			if(!inverse) vec[(size_t)i*bs + k] = tv[(size_t)ord[i]*bs + k];
+			else vec[(size_t)ord[i]*bs + k] = tv[(size_t)i*bs + k];
+		}
+	free(tv);
+}
+
+/* src/reorderingscaling.cpp:282-337 */
+void orc_scale_matrix(int bs, int nbrows, const int *browptr, const int *bcolind, double *vals,
+                      const double *rowscale, const double *colscale, int inverse)
+{
+	const int bs2 = bs*bs;
+	if(rowscale)
+		for(int i = 0; i < nbrows; i++)
+			for(int jj = browptr[i]; jj < browptr[i+1]; jj++)
+				for(int k = 0; k < bs2; k++) {
+					if(!inverse) vals[(size_t)jj*bs2 + k] *= rowscale[i];
+					else vals[(size_t)jj*bs2 + k] /= rowscale[i];
+				}
+	if(colscale)
+		for(int i = 0; i < nbrows; i++)
+			for(int jj = browptr[i]; jj < browptr[i+1]; jj++)
+				for(int k = 0; k < bs2; k++) {
+					if(!inverse) vals[(size_t)jj*bs2 + k] *= colscale[bcolind[jj]];
+					else vals[(size_t)jj*bs2 + k] /= colscale[bcolind[jj]];
+				}
+}
+
+/* src/reorderingscaling.cpp:340-368 */
+void orc_scale_vector(int bs, int n, const double *scale, int inverse, double *vec)
+{
+	if(!scale) return;
+	for(int i = 0; i < n; i++)
+		for(int k = 0; k < bs; k++) {
+			if(!inverse) vec[(size_t)i*bs + k] *= scale[i];
+			else vec[(size_t)i*bs + k] /= scale[i];
+		}
+}

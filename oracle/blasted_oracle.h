@@ -140,6 +140,27 @@ void orc_jacobi_relax(int bs, int rowmajor, int nbrows, const int *browptr, cons
 void orc_diagonal_dominance(int bs, int rowmajor, int nbrows, const int *browptr, const int *diagind,
                             const double *vals, double out[4]);
 
+/* ---- front end ---- */
+
+/* Coordinate triplets -> CSR/BSR: sort by row then column (src/coomatrix.cpp:222-260), then
+ * convertToCSR (:262-297) / convertToBSR<bs,stor> (:299-403: block columns of a block row in order of
+ * first appearance while scanning its scalar rows, blocks zero-filled, diagind = -1 where absent).
+ * Call with bcolind == NULL to get the number of stored blocks; arrays sized by that on the 2nd call. */
+long long orc_coo_convert(int nrows, long long nnz, const int *rowind, const int *colind,
+                          const double *val, int bs, int rowmajor, int *browptr, int *bcolind,
+                          int *diagind, double *vals);
+
+/* Reordering::applyOrdering, matrix (src/reorderingscaling.cpp:77-205), in place; either ordering
+ * may be NULL; diagind is not touched (nor is it in the reference) */
+void orc_reorder_matrix(int bs, int nbrows, int *browptr, int *bcolind, double *vals,
+                        const int *rord, const int *cord, int inverse);
+/* Reordering::applyOrdering, vector (:211-266): forward v[i] <- v[ord[i]], inverse v[ord[i]] <- v[i] */
+void orc_reorder_vector(int bs, int n, const int *ord, int inverse, double *vec);
+/* ReorderingScaling::applyScaling, matrix (:282-337) and vector (:340-368) */
+void orc_scale_matrix(int bs, int nbrows, const int *browptr, const int *bcolind, double *vals,
+                      const double *rowscale, const double *colscale, int inverse);
+void orc_scale_vector(int bs, int n, const double *scale, int inverse, double *vec);
+
 #ifdef __cplusplus
 }
 #endif

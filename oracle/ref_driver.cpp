@@ -29,6 +29,8 @@
 #include "levelschedule.hpp"
 #include "async_ilu_factor.hpp"
 #include "async_blockilu_factor.hpp"
+#include "coomatrix.hpp"
+#include "reorderingscaling.hpp"
 #include "../tests/solvers.hpp"
 #include "../blasted_b200/host/b200_solverops.hpp"
 
@@ -78,6 +80,42 @@ struct CoutMute {
 	CoutMute() { old = std::cout.rdbuf(sink.rdbuf()); }
 	~CoutMute() { std::cout.rdbuf(old); }
 };
+
+// front end: the reference's Reordering/ReorderingScaling are abstract (compute() comes from an
+// external ordering package); this subclass only lets the driver set the vectors they apply
+template <int bs>
+struct SetOrderingScaling : public ReorderingScaling<double,int,bs> {
+	void compute(const CRawBSRMatrix<double,int>&) override { }
+	void setScaling(const double *rs, const double *cs, const int n) {
+		if(rs) this->rowscale.assign(rs, rs + n);
+		if(cs) this->colscale.assign(cs, cs + n);
+	}
+};
+
+template <int bs>
+void ref_reorder_scale(int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
+                       const int *rord, const int *cord, const double *rs, const double *cs,
+                       int inverse, double *rowvec, double *colvec)
+{
+	SetOrderingScaling<bs> r;
+	r.setOrdering(rord, cord, nbrows);
+	r.setScaling(rs, cs, nbrows);
+	const RSApplyMode mode = inverse ? INVERSE : FORWARD;
+	if(browptr) {
+		RawBSRMatrix<double,int> mat(browptr, bcolind, vals, diagind, browptr+1, nbrows,
+		                             browptr[nbrows], browptr[nbrows]);
+		if(rs || cs) r.applyScaling(mat, mode);
+		if(rord || cord) r.applyOrdering(mat, mode);
+	}
+	if(rowvec) {
+		if(rs) r.applyScaling(rowvec, mode, ROW);
+		if(rord) r.applyOrdering(rowvec, mode, ROW);
+	}
+	if(colvec) {
+		if(cs) r.applyScaling(colvec, mode, COLUMN);
+		if(cord) r.applyOrdering(colvec, mode, COLUMN);
+	}
+}
 
 }
 
@@ -360,6 +398,58 @@ int ref_solve(const char *solver, void *prechandle, int bs, int rowmajor,
 		if(walltime) *walltime = info.walltime;
 		delete s;
 		delete A;
+	} catch(std::exception& e) { g_err = e.what(); return 1; }
+	return 0;
+}
+
+
+// ---- front end: COOMatrix::readMatrixMarket + getSRMatrixFromCOO (src/coomatrix.cpp:189-443)
+
+struct RefSRMat {
+	SRMatrixStorage<double,int> m; int bs;
+	RefSRMat(SRMatrixStorage<double,int>&& mm, int b) : m(std::move(mm)), bs(b) { }
+};
+
+void *ref_read_mtx(const char *file, int bs, int rowmajor)
+{
+	try {
+		CoutMute mute;
+		COOMatrix<double,int> coo;
+		coo.readMatrixMarket(file);
+		const std::string so = rowmajor ? "rowmajor" : "colmajor";
+		if(bs == 1) return new RefSRMat(getSRMatrixFromCOO<double,int,1>(coo, so), bs);
+		if(bs == 3) return new RefSRMat(getSRMatrixFromCOO<double,int,3>(coo, so), bs);
+		if(bs == 4) return new RefSRMat(getSRMatrixFromCOO<double,int,4>(coo, so), bs);
+		if(bs == 7) return new RefSRMat(getSRMatrixFromCOO<double,int,7>(coo, so), bs);
+		g_err = "getSRMatrixFromCOO: only bs 1,3,4,7 instantiated in the reference";
+		return nullptr;
+	} catch(std::exception& e) { g_err = e.what(); return nullptr; }
+}
+int ref_srmat_nbrows(void *hh) { return static_cast<RefSRMat*>(hh)->m.nbrows; }
+int ref_srmat_nnzb(void *hh) { return static_cast<RefSRMat*>(hh)->m.nnzb; }
+void ref_srmat_copy(void *hh, int *browptr, int *bcolind, int *diagind, double *vals)
+{
+	RefSRMat *h = static_cast<RefSRMat*>(hh);
+	const int n = h->m.nbrows, nz = h->m.nnzb, bs2 = h->bs*h->bs;
+	for(int i = 0; i <= n; i++) browptr[i] = h->m.browptr[i];
+	for(int i = 0; i < n; i++) diagind[i] = h->m.diagind[i];
+	for(int i = 0; i < nz; i++) bcolind[i] = h->m.bcolind[i];
+	for(long long i = 0; i < (long long)nz*bs2; i++) vals[i] = h->m.vals[i];
+}
+void ref_srmat_destroy(void *hh) { delete static_cast<RefSRMat*>(hh); }
+
+/// Reordering / ReorderingScaling (src/reorderingscaling.cpp) applied in place to a matrix (may be
+/// null) and to a row-direction and a column-direction vector (may be null).  Scaling is applied
+/// before the ordering, to the arrays as they are numbered on entry.
+int ref_reorder_scale(int bs, int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
+                      const int *rord, const int *cord, const double *rowscale, const double *colscale,
+                      int inverse, double *rowvec, double *colvec)
+{
+	try {
+		if(bs == 1) ref_reorder_scale<1>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else if(bs == 4) ref_reorder_scale<4>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else if(bs == 7) ref_reorder_scale<7>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else { g_err = "Reordering: only bs 1,4,7 instantiated in the reference"; return 1; }
 	} catch(std::exception& e) { g_err = e.what(); return 1; }
 	return 0;
 }
