@@ -119,8 +119,66 @@ def report(title, m, nb=3, na=3, scale=False, sgs=False, levels=False, solve=Non
                   f"rel. residual {info.resnorm/info.bnorm:.1e}, max error {float((xs-1).abs().max()):.1e}")
 
 
+def frontend_report():
+    """Front end: device conversion / reordering times on the C2 matrix, with
+    the CPU restatement of the reference algorithm (oracle, 1 thread) on a 1/16 sample beside it."""
+    import ctypes as C
+    from blasted_b200._lib import lib, check
+    from blasted_b200.frontend import Reordering, FORWARD, INVERSE
+    m = matgen.block_stencil((1024, 1024), 4, 20261020)
+    nb = m.nbrows
+    rows = torch.repeat_interleave(torch.arange(nb, device="cuda", dtype=torch.int32),
+                                   torch.as_tensor(np.diff(m.browptr), device="cuda"))
+    cols = torch.as_tensor(m.bcolind, device="cuda")
+    k = torch.arange(16, device="cuda", dtype=torch.int32)
+    r = (rows[:, None]*4 + (k % 4)[None, :]).reshape(-1)
+    c = (cols[:, None]*4 + (k // 4)[None, :]).reshape(-1)
+    v = torch.as_tensor(m.vals, device="cuda")
+    p = torch.randperm(r.numel(), device="cuda")
+    r, c, v = r[p].contiguous(), c[p].contiguous(), v[p].contiguous()
+    del p, rows, cols
+    nnz = r.numel()
+    print("\n### Front end - coordinate input and reordering on the C2 matrix\n")
+    ts = []
+    for _ in range(4):
+        h = C.c_void_p()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        check(lib.b200_mat_create_coo(m.dim, nnz, C.c_void_p(r.data_ptr()), C.c_void_p(c.data_ptr()),
+                                      C.c_void_p(v.data_ptr()), 4, 0, 1, C.byref(h)))
+        torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+        view = bb.SRMatrixView.__new__(bb.SRMatrixView); view._h = h
+        if _ < 3:
+            lib.b200_mat_destroy(h)
+    t_conv = min(ts[1:])
+    print(f"{nnz/1e6:.1f} M scrambled scalar triplets (device-resident) -> BSR4, {nb} block rows, {m.nnzb} blocks: "
+          f"{t_conv*1e3:.1f} ms ({nnz*16/t_conv/1e9:.0f} GB/s of triplets)")
+    perm = torch.randperm(nb, device="cuda").to(torch.int32)
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        check(lib.b200_mat_reorder(h, C.c_void_p(perm.data_ptr()), C.c_void_p(perm.data_ptr()), 0, 1))
+        check(lib.b200_mat_reorder(h, C.c_void_p(perm.data_ptr()), C.c_void_p(perm.data_ptr()), 1, 1))
+        torch.cuda.synchronize(); ts.append((time.perf_counter() - t0)/2)
+    print(f"\nsymmetric random permutation of the resident matrix (rows + columns, re-sorted, diagonals "
+          f"located again): {min(ts)*1e3:.1f} ms per application ({m.nnzb*128*2/min(ts)/1e9:.0f} GB/s of blocks moved)")
+    lib.b200_mat_destroy(h)
+    try:
+        from oracle import orc
+        sub = matgen.block_stencil((256, 256), 4, 20261020)
+        sp = sub.to_scipy().tocoo()
+        q = np.random.default_rng(0).permutation(sp.nnz)
+        rr, cc, vv = sp.row[q].astype(np.int32), sp.col[q].astype(np.int32), sp.data[q]
+        t0 = time.perf_counter(); orc().coo_convert(sub.dim, rr, cc, vv, 4, False); t1 = time.perf_counter() - t0
+        pp = np.random.default_rng(1).permutation(sub.nbrows).astype(np.int32)
+        t0 = time.perf_counter(); orc().reorder_matrix(sub, pp, pp, False); t2 = time.perf_counter() - t0
+        print(f"\nCPU restatement of the reference algorithm (oracle, 1 thread) on the 256x256-cell sample "
+              f"(1/16 of the work): conversion {t1*1e3:.0f} ms, permutation {t2*1e3:.0f} ms")
+    except Exception as e:                              # noqa: BLE001
+        print(f"\n(oracle not available for the CPU comparison: {e})")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
+    which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "frontend"]
     print(f"# Per-kernel throughput on the BASELINE configs ({torch.cuda.get_device_name(0)})")
     if "c1" in which:
         report("C1 - 7-point Poisson 256^3, CSR", matgen.poisson3d(256), solve=(5, 5), levels=True, sgs=True)
@@ -130,3 +188,5 @@ if __name__ == "__main__":
         report("C3 - BSR bs=5, 128^3 cells", matgen.block_stencil((128, 128, 128), 5, 20261021), sgs=True, solve=(3, 3))
     if "c4" in which:
         report("C4 - 27-point Poisson 192^3, CSR (scaled)", matgen.poisson3d(192, 27), scale=True, levels=True, sgs=True, solve=(10, 20))
+    if "frontend" in which:
+        frontend_report()
