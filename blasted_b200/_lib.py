@@ -48,6 +48,7 @@ SYMBOLS = {
     "b200_mat_nbrows": (_i, [_vp]),
     "b200_mat_nnzb": (_ll, [_vp]),
     "b200_mat_set_stream": (_i, [_vp, _vp]),
+    "b200_mat_release_workspace": (_i, [_vp]),
     "b200_mat_create_coo": (_i, [_i, _ll, _vp, _vp, _vp, _i, _i, _i, _pp]),
     "b200_mat_get_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_mat_reorder": (_i, [_vp, _vp, _vp, _i, _i]),

@@ -138,6 +138,7 @@ struct LocalOps : public KrylovOps {
 	LocalOps(const Mat *A_, Prec *M_) : A(A_), M(M_) {
 		n = A->dim();
 		stream = A->stream;
+		ws = &A->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
 		dout.alloc(MAX_DOTS);
 	}
@@ -270,6 +271,13 @@ int b200_mat_dim(const b200_mat *m) { return m->m.dim(); }
 int b200_mat_nbrows(const b200_mat *m) { return m->m.nbrows; }
 long long b200_mat_nnzb(const b200_mat *m) { return m->m.nnzb; }
 int b200_mat_set_stream(b200_mat *m, void *s) { m->m.stream = (cudaStream_t)s; return 0; }
+int b200_mat_release_workspace(b200_mat *m)
+{
+	return guarded([&] {
+		B200_CUDA(cudaStreamSynchronize(m->m.stream));
+		m->m.krylov_ws.release();
+	});
+}
 
 // ---- front end (frontend.cu): coordinate input, permutation, scaling
 

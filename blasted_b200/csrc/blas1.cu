@@ -70,6 +70,49 @@ multi_dot_stage1(const long long n, const DotPtrs p, double *__restrict__ partia
 	}
 }
 
+/// The Gram-Schmidt case: every product is against the same vector w.  w is read once per element
+/// (the general kernel would request it ND times), two elements per thread and iteration as one
+/// 16-byte load per vector.
+template <int ND>
+__global__ void __launch_bounds__(256)
+multi_dot_common_stage1(const long long n, const DotPtrs p, double *__restrict__ partial)
+{
+	double acc[ND];
+#pragma unroll
+	for(int d = 0; d < ND; d++) acc[d] = 0;
+	const double *__restrict__ w = p.b[0];
+	const long long n2 = n >> 1;
+	for(long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n2;
+	    i += (long long)gridDim.x*blockDim.x)
+	{
+		const double2 wv = __ldg(reinterpret_cast<const double2*>(w) + i);
+		double2 av[ND];
+#pragma unroll
+		for(int d = 0; d < ND; d++) av[d] = __ldg(reinterpret_cast<const double2*>(p.a[d]) + i);
+#pragma unroll
+		for(int d = 0; d < ND; d++) acc[d] = fma(av[d].y, wv.y, fma(av[d].x, wv.x, acc[d]));
+	}
+	if((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+		for(int d = 0; d < ND; d++) acc[d] = fma(p.a[d][n-1], w[n-1], acc[d]);
+	}
+	__shared__ double sm[ND][8];
+	const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+	for(int d = 0; d < ND; d++) {
+		double v = acc[d];
+#pragma unroll
+		for(int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+		if(lane == 0) sm[d][wp] = v;
+	}
+	__syncthreads();
+	if(threadIdx.x < ND) {
+		double t = 0;
+		for(int i = 0; i < 8; i++) t += sm[threadIdx.x][i];
+		partial[threadIdx.x*DOT_BLOCKS + blockIdx.x] = t;
+	}
+}
+
 __global__ void __launch_bounds__(256)
 multi_dot_stage2(const int nd, const int nblocks, const double *__restrict__ partial,
                  double *__restrict__ out)
@@ -98,24 +141,21 @@ void launch_multi_dot(long long n, int nd, const double *const *a, const double 
 	DotPtrs p;
 	for(int d = 0; d < MAX_DOTS; d++) { p.a[d] = a[d < nd ? d : 0]; p.b[d] = b[d < nd ? d : 0]; }
 	const int grid = (int)std::max<long long>(1, std::min<long long>(DOT_BLOCKS, div_up(n, 256)));
+	// all products against one 16-byte aligned vector: the Gram-Schmidt form
+	bool common = nd > 1 && (reinterpret_cast<size_t>(b[0]) & 15) == 0;
+	for(int d = 0; d < nd && common; d++)
+		common = (b[d] == b[0]) && (reinterpret_cast<size_t>(a[d]) & 15) == 0;
+#define B200_DOT_CASE(K) \
+	case K: if(common) multi_dot_common_stage1<K><<<grid,256,0,st>>>(n, p, d_partial); \
+	        else multi_dot_stage1<K><<<grid,256,0,st>>>(n, p, d_partial); break;
 	switch(nd) {
-	case 1: multi_dot_stage1<1><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 2: multi_dot_stage1<2><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 3: multi_dot_stage1<3><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 4: multi_dot_stage1<4><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 5: multi_dot_stage1<5><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 6: multi_dot_stage1<6><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 7: multi_dot_stage1<7><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 8: multi_dot_stage1<8><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 9: multi_dot_stage1<9><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 10: multi_dot_stage1<10><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 11: multi_dot_stage1<11><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 12: multi_dot_stage1<12><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 13: multi_dot_stage1<13><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 14: multi_dot_stage1<14><<<grid,256,0,st>>>(n, p, d_partial); break;
-	case 15: multi_dot_stage1<15><<<grid,256,0,st>>>(n, p, d_partial); break;
-	default: multi_dot_stage1<16><<<grid,256,0,st>>>(n, p, d_partial); break;
+	B200_DOT_CASE(1) B200_DOT_CASE(2) B200_DOT_CASE(3) B200_DOT_CASE(4) B200_DOT_CASE(5)
+	B200_DOT_CASE(6) B200_DOT_CASE(7) B200_DOT_CASE(8) B200_DOT_CASE(9) B200_DOT_CASE(10)
+	B200_DOT_CASE(11) B200_DOT_CASE(12) B200_DOT_CASE(13) B200_DOT_CASE(14) B200_DOT_CASE(15)
+	default: if(common) multi_dot_common_stage1<16><<<grid,256,0,st>>>(n, p, d_partial);
+	         else multi_dot_stage1<16><<<grid,256,0,st>>>(n, p, d_partial); break;
 	}
+#undef B200_DOT_CASE
 	B200_LAUNCHED();
 	multi_dot_stage2<<<1,256,0,st>>>(nd, grid, d_partial, d_out);
 	B200_LAUNCHED();

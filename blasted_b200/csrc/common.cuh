@@ -116,6 +116,7 @@ struct Mat {
 	cudaStream_t stream = 0;
 	mutable DevBuf<double> hx, hy, hz;    ///< staging for the *_host entry points
 	DevBuf<double> stage;                 ///< fixed staging buffer for layout-converting uploads
+	mutable DevBuf<double> krylov_ws;     ///< Krylov basis storage, kept between solves (grow-only)
 
 	int dim() const { return nbrows*bs; }
 };
@@ -340,6 +341,16 @@ struct KrylovOps {
 	/// out[i] = a[i].b[i], i < nd, summed over all ranks, returned on the host; the return value
 	/// points to the same results in device memory (valid until the next call)
 	virtual const double *dots(int nd, const double *const *a, const double *const *b, double *out) = 0;
+	/// Basis storage for the restarted solvers.  Taken from a buffer that outlives the solve (the
+	/// operator's) when there is one: allocating and freeing gigabytes inside every solve costs
+	/// tens of milliseconds of idle GPU.
+	DevBuf<double> *ws = nullptr;
+	DevBuf<double> own_ws;
+	double *workspace(size_t count) {
+		DevBuf<double>& b = ws ? *ws : own_ws;
+		if(b.n < count) b.alloc(count);
+		return b.p;
+	}
 };
 
 void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, double *d_x,

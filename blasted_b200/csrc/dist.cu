@@ -135,6 +135,7 @@ struct DistOps : public KrylovOps {
 	DistOps(DistMat *D_, Prec *M_) : D(D_), M(M_) {
 		n = D->diag->dim();
 		stream = D->stream;
+		ws = &D->diag->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
 		dout.alloc(MAX_DOTS);
 	}

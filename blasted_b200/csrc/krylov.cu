@@ -123,12 +123,15 @@ void gcr(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, in
 	const long long n = ops.n;
 	cudaStream_t st = ops.stream;
 	if(nrestart < 1) throw Error("GCR: restart length must be positive");
-	DevBuf<double> res, z, pbuf, qbuf, dcoef;
-	res.alloc(n); z.alloc(n);
-	pbuf.alloc((size_t)n*nrestart); qbuf.alloc((size_t)n*nrestart);
+	DevBuf<double> dcoef;
+	double *const base = ops.workspace((size_t)n*(2*(size_t)nrestart + 2));
+	double *const res = base, *const z = base + n;
 	dcoef.alloc(2*(size_t)nrestart);
 	std::vector<double*> p(nrestart), q(nrestart);
-	for(int i = 0; i < nrestart; i++) { p[i] = pbuf.p + (size_t)i*n; q[i] = qbuf.p + (size_t)i*n; }
+	for(int i = 0; i < nrestart; i++) {
+		p[i] = base + (size_t)(2 + i)*n;
+		q[i] = base + (size_t)(2 + nrestart + i)*n;
+	}
 	std::vector<double> qq(nrestart, 0.0), beta(nrestart, 0.0);
 
 	const double bnorm = std::sqrt(dot1(ops, b, b));
@@ -196,11 +199,11 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 	const long long n = ops.n;
 	cudaStream_t st = ops.stream;
 	if(m < 1) throw Error("FGMRES: restart length must be positive");
-	DevBuf<double> vbuf, zbuf, w;
-	vbuf.alloc((size_t)n*(m+1)); zbuf.alloc((size_t)n*m); w.alloc(n);
+	double *const base = ops.workspace((size_t)n*(2*(size_t)m + 2));
+	double *const w = base + (size_t)(2*(size_t)m + 1)*n;
 	std::vector<double*> V(m+1), Z(m);
-	for(int i = 0; i <= m; i++) V[i] = vbuf.p + (size_t)i*n;
-	for(int i = 0; i < m; i++) Z[i] = zbuf.p + (size_t)i*n;
+	for(int i = 0; i <= m; i++) V[i] = base + (size_t)i*n;
+	for(int i = 0; i < m; i++) Z[i] = base + (size_t)(m + 1 + i)*n;
 	std::vector<double> H((size_t)(m+1)*m, 0.0), cs(m), sn(m), g(m+1), y(m);
 	DevBuf<double> dy;
 	dy.alloc(m);

@@ -200,6 +200,10 @@ class SRMatrixView:
     def set_stream(self, stream_ptr: int) -> None:
         lib.b200_mat_set_stream(self._h, C.c_void_p(stream_ptr))
 
+    def release_workspace(self) -> None:
+        """Frees the Krylov basis storage the solvers keep with the operator between solves."""
+        check(lib.b200_mat_release_workspace(self._h))
+
     def close(self):
         if self._h:
             lib.b200_mat_destroy(self._h)

@@ -119,6 +119,9 @@ int b200_mat_dim(const b200_mat *m);            /* nbrows*bs, as MatrixView::dim
 int b200_mat_nbrows(const b200_mat *m);
 long long b200_mat_nnzb(const b200_mat *m);
 int b200_mat_set_stream(b200_mat *m, void *cuda_stream);
+/** The restarted Krylov drivers keep their basis storage with the operator between solves
+ *  (n*(2*restart+2) doubles, grow-only); this frees it. */
+int b200_mat_release_workspace(b200_mat *m);
 
 /* ---- front end: the step before the path.  Every array argument is
  *      a host pointer when on_device == 0 and a device pointer otherwise. ---- */
