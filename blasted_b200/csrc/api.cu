@@ -140,7 +140,7 @@ struct LocalOps : public KrylovOps {
 		stream = A->stream;
 		ws = &A->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
-		dout.alloc(MAX_DOTS);
+		dout.alloc(MAX_KRYLOV_DOTS);
 	}
 	void spmv(const double *x, double *y) override { launch_spmv(*A, x, y, stream); }
 	void gemv3(double a, const double *x, double b, const double *y, double *z) override {
@@ -151,7 +151,9 @@ struct LocalOps : public KrylovOps {
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
 	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
-		launch_multi_dot(n, nd, a, b, partial, dout, stream);
+		if(nd > MAX_KRYLOV_DOTS) throw Error("dots: too many products");
+		for(int o = 0; o < nd; o += MAX_DOTS)
+			launch_multi_dot(n, std::min(MAX_DOTS, nd - o), a + o, b + o, partial, dout.p + o, stream);
 		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
 		B200_CUDA(cudaStreamSynchronize(stream));
 		return dout.p;

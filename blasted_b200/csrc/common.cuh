@@ -272,6 +272,7 @@ void launch_axpbypcz(long long n, double p, double *z, double q, const double *x
                      const double *y, cudaStream_t st);
 /// out[0..nd) = dots of pairs (a[i], b[i]); result left on the device in d_out
 constexpr int MAX_DOTS = 16;
+constexpr int MAX_KRYLOV_DOTS = 64;  ///< products per KrylovOps::dots call (chunks of MAX_DOTS, one sync)
 constexpr int DOT_BLOCKS = 592;      // 148 SMs x 4
 /// d_out[i] = a[i] . b[i] for i < nd <= MAX_DOTS, deterministic two-stage reduction;
 /// d_partial must hold MAX_DOTS*DOT_BLOCKS doubles.  Result stays on the device.

@@ -137,7 +137,7 @@ struct DistOps : public KrylovOps {
 		stream = D->stream;
 		ws = &D->diag->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
-		dout.alloc(MAX_DOTS);
+		dout.alloc(MAX_KRYLOV_DOTS);
 	}
 	void spmv(const double *x, double *y) override { dist_spmv(*D, 1.0, x, 0.0, nullptr, y, true); }
 	void gemv3(double a, const double *x, double b, const double *y, double *z) override {
@@ -148,7 +148,9 @@ struct DistOps : public KrylovOps {
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
 	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
-		launch_multi_dot(n, nd, a, b, partial, dout, stream);
+		if(nd > MAX_KRYLOV_DOTS) throw Error("dots: too many products");
+		for(int o = 0; o < nd; o += MAX_DOTS)
+			launch_multi_dot(n, std::min(MAX_DOTS, nd - o), a + o, b + o, partial, dout.p + o, stream);
 		if(D->comm->world > 1)
 			B200_NCCL(g_nccl.AllReduce(dout.p, dout.p, nd, ncclFloat64, ncclSum, D->comm->comm, stream));
 		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));

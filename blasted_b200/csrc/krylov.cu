@@ -199,6 +199,8 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 	const long long n = ops.n;
 	cudaStream_t st = ops.stream;
 	if(m < 1) throw Error("FGMRES: restart length must be positive");
+	if(m + 1 > MAX_KRYLOV_DOTS)
+		throw Error("FGMRES: restart length above " + std::to_string(MAX_KRYLOV_DOTS - 1) + " not supported");
 	double *const base = ops.workspace((size_t)n*(2*(size_t)m + 2));
 	double *const w = base + (size_t)(2*(size_t)m + 1)*n;
 	std::vector<double*> V(m+1), Z(m);
@@ -224,17 +226,24 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 		for(; j < m && step < maxiter; j++) {
 			ops.prec(V[j], Z[j]);                              // z_j = M_j^-1 v_j
 			ops.spmv(Z[j], w);                                 // w = A z_j
-			// classical Gram-Schmidt: h_i = v_i . w (fused), w -= sum h_i v_i (fused)
-			for(int i0 = 0; i0 <= j; i0 += MAX_DOTS) {
-				const int nd = std::min(MAX_DOTS, j + 1 - i0);
-				const double *aa[MAX_DOTS], *bb[MAX_DOTS];
-				double out[MAX_DOTS];
-				for(int i = 0; i < nd; i++) { aa[i] = V[i0+i]; bb[i] = w; }
-				const double *dh = ops.dots(nd, aa, bb, out);
-				for(int i = 0; i < nd; i++) H[(size_t)(i0+i)*m + j] = out[i];
-				launch_multi_axpy(n, nd, V.data() + i0, dh, w, st, -1.0);
+			// classical Gram-Schmidt with ONE reduction per iteration: h_i = v_i . w and w . w in the
+			// same fused multi-dot (one all-reduce, one host synchronisation), w -= sum h_i v_i, and
+			// |w_new|^2 = w.w - sum h_i^2 because V is orthonormal.  When that difference loses
+			// more than four digits to cancellation the norm is computed explicitly instead.
+			double hn;
+			{
+				const double *aa[MAX_KRYLOV_DOTS], *bb[MAX_KRYLOV_DOTS];
+				double out[MAX_KRYLOV_DOTS];
+				for(int i = 0; i <= j; i++) { aa[i] = V[i]; bb[i] = w; }
+				aa[j+1] = w; bb[j+1] = w;
+				const double *dh = ops.dots(j + 2, aa, bb, out);
+				double sumsq = 0;
+				for(int i = 0; i <= j; i++) { H[(size_t)i*m + j] = out[i]; sumsq += out[i]*out[i]; }
+				for(int l0 = 0; l0 <= j; l0 += 32)
+					launch_multi_axpy(n, std::min(32, j + 1 - l0), V.data() + l0, dh + l0, w, st, -1.0);
+				const double ww = out[j+1], hn2 = ww - sumsq;
+				hn = (hn2 > 1e-4*ww) ? std::sqrt(hn2) : std::sqrt(dot1(ops, w, w));
 			}
-			const double hn = std::sqrt(dot1(ops, w, w));
 			H[(size_t)(j+1)*m + j] = hn;
 			if(hn > 0) launch_vec_scal(n, 1.0/hn, w, V[j+1], st);
 			// Givens rotations on column j
