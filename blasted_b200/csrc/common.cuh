@@ -15,6 +15,7 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <memory>
 #include <atomic>
 
 #include "../../include/blasted_b200.h"
@@ -100,6 +101,25 @@ struct DevBuf {
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1)/b); }
 
+/// Vectors for the restarted Krylov drivers, allocated a few at a time as the basis grows (a
+/// solve that converges in 4 iterations should not pay for 62 vectors) and kept between solves.
+struct KrylovStore {
+	static constexpr int PER_CHUNK = 8;
+	long long stride = 0;                                   ///< doubles per vector (even: 16-byte aligned)
+	std::vector<std::unique_ptr<DevBuf<double>>> chunks;
+	void release() { chunks.clear(); stride = 0; }
+	double *vec(long long n, int i) {
+		const long long need = (n + 1) & ~1LL;
+		if(need != stride) { release(); stride = need; }
+		const size_t c = (size_t)i / PER_CHUNK;
+		while(chunks.size() <= c) {
+			chunks.emplace_back(new DevBuf<double>());
+			chunks.back()->alloc((size_t)std::max<long long>(stride, 2)*PER_CHUNK);
+		}
+		return chunks[c]->p + (size_t)(i % PER_CHUNK)*stride;
+	}
+};
+
 // ---------------------------------------------------------------- the matrix
 
 /// Device-resident sparse (block-)row matrix.  Blocks are column-major on the device.
@@ -116,7 +136,7 @@ struct Mat {
 	cudaStream_t stream = 0;
 	mutable DevBuf<double> hx, hy, hz;    ///< staging for the *_host entry points
 	DevBuf<double> stage;                 ///< fixed staging buffer for layout-converting uploads
-	mutable DevBuf<double> krylov_ws;     ///< Krylov basis storage, kept between solves (grow-only)
+	mutable KrylovStore krylov_ws;        ///< Krylov basis storage, kept between solves (grow-only)
 
 	int dim() const { return nbrows*bs; }
 };
@@ -345,13 +365,9 @@ struct KrylovOps {
 	/// Basis storage for the restarted solvers.  Taken from a buffer that outlives the solve (the
 	/// operator's) when there is one: allocating and freeing gigabytes inside every solve costs
 	/// tens of milliseconds of idle GPU.
-	DevBuf<double> *ws = nullptr;
-	DevBuf<double> own_ws;
-	double *workspace(size_t count) {
-		DevBuf<double>& b = ws ? *ws : own_ws;
-		if(b.n < count) b.alloc(count);
-		return b.p;
-	}
+	KrylovStore *ws = nullptr;
+	KrylovStore own_ws;
+	double *work_vec(int i) { return (ws ? *ws : own_ws).vec(n, i); }
 };
 
 void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, double *d_x,

@@ -124,14 +124,12 @@ void gcr(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, in
 	cudaStream_t st = ops.stream;
 	if(nrestart < 1) throw Error("GCR: restart length must be positive");
 	DevBuf<double> dcoef;
-	double *const base = ops.workspace((size_t)n*(2*(size_t)nrestart + 2));
-	double *const res = base, *const z = base + n;
+	// basis vectors come from the operator's store as they are first needed (p_i, q_i interleaved)
+	double *const res = ops.work_vec(0), *const z = ops.work_vec(1);
 	dcoef.alloc(2*(size_t)nrestart);
-	std::vector<double*> p(nrestart), q(nrestart);
-	for(int i = 0; i < nrestart; i++) {
-		p[i] = base + (size_t)(2 + i)*n;
-		q[i] = base + (size_t)(2 + nrestart + i)*n;
-	}
+	std::vector<double*> p(nrestart, nullptr), q(nrestart, nullptr);
+	auto need = [&](int i) { if(!p[i]) { p[i] = ops.work_vec(2 + 2*i); q[i] = ops.work_vec(3 + 2*i); } };
+	need(0);
 	std::vector<double> qq(nrestart, 0.0), beta(nrestart, 0.0);
 
 	const double bnorm = std::sqrt(dot1(ops, b, b));
@@ -158,6 +156,7 @@ void gcr(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, in
 			if(k == nrestart-1) break;
 			if(step >= maxiter) break;
 
+			need(k+1);
 			ops.prec(res, z);
 			ops.spmv(z, q[k+1]);
 			B200_CUDA(cudaMemcpyAsync(p[k+1], z, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -201,11 +200,14 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 	if(m < 1) throw Error("FGMRES: restart length must be positive");
 	if(m + 1 > MAX_KRYLOV_DOTS)
 		throw Error("FGMRES: restart length above " + std::to_string(MAX_KRYLOV_DOTS - 1) + " not supported");
-	double *const base = ops.workspace((size_t)n*(2*(size_t)m + 2));
-	double *const w = base + (size_t)(2*(size_t)m + 1)*n;
-	std::vector<double*> V(m+1), Z(m);
-	for(int i = 0; i <= m; i++) V[i] = base + (size_t)i*n;
-	for(int i = 0; i < m; i++) Z[i] = base + (size_t)(m + 1 + i)*n;
+	// basis vectors come from the operator's store as they are first needed (w, v_0, z_0, v_1, ...)
+	double *const w = ops.work_vec(0);
+	std::vector<double*> V(m+1, nullptr), Z(m, nullptr);
+	auto need = [&](int i) {
+		if(!V[i]) V[i] = ops.work_vec(1 + 2*i);
+		if(i < m && !Z[i]) Z[i] = ops.work_vec(2 + 2*i);
+	};
+	need(0);
 	std::vector<double> H((size_t)(m+1)*m, 0.0), cs(m), sn(m), g(m+1), y(m);
 	DevBuf<double> dy;
 	dy.alloc(m);
@@ -224,6 +226,7 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 		g[0] = beta;
 		int j = 0;
 		for(; j < m && step < maxiter; j++) {
+			need(j+1);
 			ops.prec(V[j], Z[j]);                              // z_j = M_j^-1 v_j
 			ops.spmv(Z[j], w);                                 // w = A z_j
 			// classical Gram-Schmidt with ONE reduction per iteration: h_i = v_i . w and w . w in the

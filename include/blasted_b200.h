@@ -120,7 +120,7 @@ int b200_mat_nbrows(const b200_mat *m);
 long long b200_mat_nnzb(const b200_mat *m);
 int b200_mat_set_stream(b200_mat *m, void *cuda_stream);
 /** The restarted Krylov drivers keep their basis storage with the operator between solves
- *  (n*(2*restart+2) doubles, grow-only); this frees it. */
+ *  (up to 2*restart+2 vectors, allocated eight at a time as the basis grows); this frees it. */
 int b200_mat_release_workspace(b200_mat *m);
 
 /* ---- front end: the step before the path.  Every array argument is

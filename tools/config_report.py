@@ -146,7 +146,6 @@ def frontend_report():
         check(lib.b200_mat_create_coo(m.dim, nnz, C.c_void_p(r.data_ptr()), C.c_void_p(c.data_ptr()),
                                       C.c_void_p(v.data_ptr()), 4, 0, 1, C.byref(h)))
         torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-        view = bb.SRMatrixView.__new__(bb.SRMatrixView); view._h = h
         if _ < 3:
             lib.b200_mat_destroy(h)
     t_conv = min(ts[1:])
