@@ -97,16 +97,38 @@ struct DistMat {
 	DevBuf<int> send_idx;                       ///< local (block) rows to send, grouped by neighbour
 	DevBuf<double> send_buf, halo;
 	cudaStream_t stream = 0;
+	// the exchange runs on its own stream so that it overlaps the diagonal-block product
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+	void ensure_comm_stream() {
+		if(comm_stream) return;
+		B200_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+		B200_CUDA(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
+		B200_CUDA(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
+	}
+	~DistMat() {
+		if(ev_packed) cudaEventDestroy(ev_packed);
+		if(ev_halo) cudaEventDestroy(ev_halo);
+		if(comm_stream) cudaStreamDestroy(comm_stream);
+	}
 };
 
-static void halo_exchange(DistMat& D, const double *x)
+/// Packs the boundary rows on the compute stream and posts the sends/receives on the exchange
+/// stream; returns true if an exchange is in flight (the caller waits on ev_halo before it reads
+/// the halo).  Buffer reuse is ordered by the same two events: the next pack follows the wait on
+/// ev_halo (sends done), the next receive follows ev_packed (previous halo reads done).  Only one
+/// NCCL operation of the communicator is ever in flight (the all-reduces follow the product).
+static bool halo_exchange(DistMat& D, const double *x)
 {
-	cudaStream_t st = D.stream;
 	if(D.nsend > 0) {
-		pack_kernel<<<div_up(D.nsend*D.bs, 256), 256, 0, st>>>(D.nsend, D.bs, D.send_idx, x, D.send_buf);
+		pack_kernel<<<div_up(D.nsend*D.bs, 256), 256, 0, D.stream>>>(D.nsend, D.bs, D.send_idx, x, D.send_buf);
 		B200_LAUNCHED();
 	}
-	if(D.neigh.empty()) return;
+	if(D.neigh.empty()) return false;
+	D.ensure_comm_stream();
+	cudaStream_t st = D.comm_stream;
+	B200_CUDA(cudaEventRecord(D.ev_packed, D.stream));
+	B200_CUDA(cudaStreamWaitEvent(st, D.ev_packed, 0));
 	B200_NCCL(g_nccl.GroupStart());
 	size_t so = 0, ro = 0;
 	for(size_t k = 0; k < D.neigh.size(); k++) {
@@ -116,14 +138,17 @@ static void halo_exchange(DistMat& D, const double *x)
 		so += ns; ro += nr;
 	}
 	B200_NCCL(g_nccl.GroupEnd());
+	B200_CUDA(cudaEventRecord(D.ev_halo, st));
+	return true;
 }
 
 static void dist_spmv(DistMat& D, double a, const double *x, double b, const double *y, double *z,
                       bool plain)
 {
-	halo_exchange(D, x);
-	if(plain) launch_spmv(*D.diag, x, z, D.stream);
+	const bool inflight = halo_exchange(D, x);
+	if(plain) launch_spmv(*D.diag, x, z, D.stream);      // overlaps the exchange
 	else launch_gemv3(*D.diag, a, x, b, y, z, D.stream);
+	if(inflight) B200_CUDA(cudaStreamWaitEvent(D.stream, D.ev_halo, 0));
 	if(D.offd && D.offd->nnzb > 0)                       // z += a * A_offd * halo
 		launch_gemv3(*D.offd, plain ? 1.0 : a, D.halo, 1.0, z, z, D.stream);
 }
