@@ -50,6 +50,7 @@ void prec_compute(Prec& P, double precinfo[6])
 	if(precinfo) for(int i = 0; i < 6; i++) precinfo[i] = 0;     // PrecInfo() value-initialised
 
 	if(type == B200_NO_PREC) { P.computed = true; return; }
+	if(A.nbrows == 0) { P.computed = true; return; }          // empty subdomain: nothing to build
 	if(!A.has_diag) throw Error("preconditioner needs a structurally non-zero diagonal");
 	if(!P.scratch.p) P.scratch.alloc(8);
 
@@ -258,6 +259,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 	const long long n = A.dim();
 	ensure_events(P);
 	if(type != B200_NO_PREC && !P.computed) throw Error("apply() called before compute()");
+	if(n == 0) return;
 	B200_CUDA(cudaEventRecord(P.ev0, st));
 
 	if(type == B200_NO_PREC) {
@@ -399,6 +401,7 @@ void prec_apply_relax(Prec& P, const double *b, double *x, int maxits)
 	if(type == B200_NO_PREC) return;                      // NoPreconditioner::apply_relax: nothing
 	if(P.is_ilu) throw Error("ILU relaxation not implemented!");   // solverops_ilu0.cpp:215,382
 	if(!P.computed) throw Error("apply_relax() called before compute()");
+	if(n == 0) return;
 
 	TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.rhs = b; a.x = x;
 	a.row_begin = 0; a.row_end = A.nbrows;
