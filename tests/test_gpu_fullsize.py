@@ -65,3 +65,60 @@ def test_poisson128_exact_vs_async_solve():
         assert relerr(x, np.ones(m.dim)) < 1e-5
         its[ptype] = info.iters
     assert abs(its["ilu0"] - its["sapilu0"]) <= max(1, int(np.ceil(0.05*its["sapilu0"])))
+
+
+def test_c3_bsr5_factor_apply_properties():
+    """BASELINE C3: BSR bs=5, 128^3 cells (2 097 152 block rows, 2.9 GB of blocks)."""
+    m = matgen.block_stencil((128, 128, 128), 5, SEED + 3)
+    assert m.nbrows == 2097152
+    view = bb.SRMatrixView(m)
+    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["ilu0"], bs=5, nbuildsweeps=1, napplysweeps=1,
+                               compute_precinfo=True)
+    p = bb.SRFactory().create_preconditioner(view, s)
+    res = []
+    for nsw in (1, 2, 4, 10):
+        p.set_sweeps(nsw, 1)
+        info = p.compute().f_info
+        res.append(info[0]/info[1])
+    assert res[0] < 1.0 and res[-1] < 1e-10 and all(b <= a*1.0001 for a, b in zip(res, res[1:]))
+    # converged sweeps: the asynchronous apply equals the level-scheduled exact substitution on
+    # the same factor, and M^-1 is a good approximate inverse of this diagonally dominant matrix
+    p.set_sweeps(10, 16)
+    p.compute()
+    rng = np.random.default_rng(SEED + 3)
+    r = rng.standard_normal(m.dim)
+    z = p.apply(r)
+    q = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["sapilu0"], bs=5, nbuildsweeps=10))
+    q.compute()
+    assert relerr(z, q.apply(r)) < 1e-9
+    assert np.linalg.norm(view.apply(z) - r) < 0.05*np.linalg.norm(r)
+    # block SGS and Jacobi on the same matrix: linear, finite, and a contraction of the residual
+    for name, bound in (("sgs", 0.2), ("jacobi", 0.6)):
+        g = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+            prectype=SOLVER_TYPES[name], bs=5, napplysweeps=12))
+        g.compute()
+        zg = g.apply(r)
+        assert np.linalg.norm(view.apply(zg) - r) < bound*np.linalg.norm(r)
+
+
+def test_c4_27point_scaled_factor_properties():
+    """BASELINE C4 stencil (27-point, diag 26, off -1) at 160^3 (4.1 M rows, 108 M entries; the
+    256^3 case of BASELINE.json is 5.4 GB of host arrays to generate - too slow for a test): the
+    nonlinear residual of the scaled factorisation decreases monotonically and the asynchronous
+    factor converges to the exact one."""
+    m = matgen.poisson3d(160, 27)
+    view = bb.SRMatrixView(m)
+    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=1, napplysweeps=1,
+                               scale=True, compute_precinfo=True)
+    p = bb.SRFactory().create_preconditioner(view, s)
+    res = []
+    for nsw in (1, 3, 10, 40):
+        p.set_sweeps(nsw, 1)
+        info = p.compute().f_info
+        res.append(info[0]/info[1])
+    assert all(b < a for a, b in zip(res, res[1:])) and res[-1] < 1e-9
+    q = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["sfilu0"], bs=1, scale=True, nbuildsweeps=1))
+    q.compute()
+    assert relerr(p.factor(), q.factor()) < 1e-9
