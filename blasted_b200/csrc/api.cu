@@ -491,7 +491,11 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z)
 			B200_CUDA(cudaMemcpyAsync(P.hz, z, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
 		prec_apply(P, P.hr, P.hz);
 		B200_CUDA(cudaMemcpyAsync(z, P.hz, n*sizeof(double), cudaMemcpyDeviceToHost, P.stream));
+		int flag = 0;
+		if(P.sync_flags.p)
+			B200_CUDA(cudaMemcpyAsync(&flag, P.sync_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, P.stream));
 		B200_CUDA(cudaStreamSynchronize(P.stream));
+		if(flag) throw Error("exact substitution did not complete: a dependency never arrived");
 	});
 }
 

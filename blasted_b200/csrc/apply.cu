@@ -330,6 +330,195 @@ void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t
 	}
 }
 
+// ------------------------------------------------------------------ exact substitution, one launch
+
+/// polled read of a value another CTA may be about to publish (never hoisted, read at L2)
+__device__ __forceinline__ double ld_poll(const double *p)
+{
+	double v;
+	asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ bool is_unset(const double v)
+{
+	return (unsigned long long)__double_as_longlong(v) == 0xffffffffffffffffull;
+}
+
+/// Exact (level-ordered) triangular substitution in ONE launch instead of one launch per level.
+/// Rows are taken in the order of the level-sorted row list; the output vector is pre-filled with
+/// an all-ones bit pattern and every value doubles as its own "ready" flag: a row consumes its
+/// dependencies x_j in column order as soon as they stop being the sentinel (polled at L2), and
+/// publishes x_i with ordinary 8-byte stores.  All dependencies of a row sit earlier in the list;
+/// CTAs take their position from a ticket counter, so every CTA a row can wait for has already
+/// started - no deadlock - and rows deep in finished levels never wait at all.  Nothing else
+/// changes: same per-row arithmetic in the same column order as tri_scalar/tri_block_kernel, one
+/// final store per value.  The spin is bounded: past the cap a warp raises *err and stops waiting
+/// (a dependency pointing forward in the list - a pattern the level builder should have refused).
+template <int BS, int KIND, bool VEC>
+__global__ void __launch_bounds__(256)
+tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ err)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	__shared__ int s_cta;
+	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long warp = (long long)s_cta*(blockDim.x >> 5) + (threadIdx.x >> 5);
+	const long long t = warp*GPW + g;
+	const int nrows = a.row_end - a.row_begin;
+	const bool valid = (g < GPW) && (t < nrows);
+	int row = 0, k = 0, je = 0;
+	const int *cols = a.bcolind;
+	double acc = 0, rhs = 0;
+	double dr[BS];
+#pragma unroll
+	for(int c = 0; c < BS; c++) dr[c] = 0;
+	if(valid) {
+		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
+		row = a.rows ? __ldg(a.rows + idx) : idx;
+		if(BS == 1 && a.part_ptr) {
+			k = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
+			cols = a.part_col;
+		} else {
+			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+			const int d = __ldg(a.diagind + row);
+			part_range<KIND>(s, d, e, k, je);
+		}
+		rhs = __ldg(a.rhs + (size_t)row*BS + r);
+		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
+		if(BS > 1 && KIND != TRI_ILU_LOWER)
+			BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
+		else if(BS == 1 && KIND != TRI_ILU_LOWER) {
+			if(KIND == TRI_ILU_UPPER)
+				dr[0] = 1.0/(a.part_ptr ? __ldg(a.part_diag + row) : __ldg(a.vals + __ldg(a.diagind + row)));
+			else dr[0] = __ldg(a.dinv + row);
+		}
+	}
+	bool stored = !valid;
+	int spins = 0;
+	while(true) {
+		if(!stored) {
+			// consume, in column order, every dependency that has been published.  The next DK
+			// dependencies are polled together (one L2 round trip, not DK) and the ready prefix
+			// is accumulated.
+			constexpr int DK = (BS == 1) ? 8 : 3;
+			while(k < je) {
+				const int nb = min(DK, je - k);
+				int col[DK];
+				double xv[DK][BS];
+#pragma unroll
+				for(int q = 0; q < DK; q++) col[q] = (q < nb) ? __ldg(cols + k + q) : 0;
+#pragma unroll
+				for(int q = 0; q < DK; q++) {
+					if(q < nb) {
+						if(BS == 4 && VEC)
+							ld256_cg_ordered(a.xsrc + (size_t)col[q]*BS, xv[q][0], xv[q][1], xv[q][2], xv[q][3]);
+						else {
+#pragma unroll
+							for(int c = 0; c < BS; c++) xv[q][c] = ld_poll(a.xsrc + (size_t)col[q]*BS + c);
+						}
+					} else {
+#pragma unroll
+						for(int c = 0; c < BS; c++) xv[q][c] = 0;
+					}
+				}
+				int adv = 0;
+#pragma unroll
+				for(int q = 0; q < DK; q++) {
+					bool unset = false;
+#pragma unroll
+					for(int c = 0; c < BS; c++) unset |= is_unset(xv[q][c]);
+					if(q < nb && adv == q && !unset) {
+						if(BS == 1) acc = fma(__ldg(a.vals + k + q), xv[q][0], acc);
+						else {
+							double av[BS];
+							BlkIO<BS>::template load_row<false>(a.vals + (size_t)(k + q)*BS2, r, av);
+#pragma unroll
+							for(int c = 0; c < BS; c++) acc = fma(av[c], xv[q][c], acc);
+						}
+						adv++;
+					}
+				}
+				k += adv;
+				if(adv < nb) break;
+			}
+		}
+		const bool fin = !stored && k == je;
+		// epilogue with the whole warp converged (the block forms exchange values by shuffles)
+		double out;
+		if(KIND == TRI_ILU_LOWER) out = rhs - acc;
+		else if(BS == 1) out = (KIND == TRI_SGS_BWD) ? rhs - dr[0]*acc : dr[0]*(rhs - acc);
+		else {
+			const double tv = (KIND == TRI_SGS_BWD) ? acc : rhs - acc;
+			double prod = 0;
+#pragma unroll
+			for(int c = 0; c < BS; c++) {
+				const double tc = __shfl_sync(0xffffffffu, tv, min(g*BS + c, 31));
+				prod = fma(dr[c], tc, prod);
+			}
+			out = (KIND == TRI_SGS_BWD) ? rhs - prod : prod;
+		}
+		if(fin) {
+			if(is_unset(out)) out = __longlong_as_double(0x7ff8000000000000ll);
+			a.x[(size_t)row*BS + r] = out;
+			stored = true;
+		}
+		if(__all_sync(0xffffffffu, stored)) break;
+		if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
+			if(spins > (1 << 22) || *((volatile int*)err)) {
+				*err = 1;
+				k = je;                               // stop waiting; the result is flagged invalid
+			}
+		}
+	}
+}
+
+template <int KIND>
+static void launch_syncfree_kind(const Mat& A, const TriDev& d, int *ticket, int *err, cudaStream_t st)
+{
+	const long long nrows = d.row_end - d.row_begin;
+	if(nrows <= 0) return;
+	B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(int), st));
+	B200_CUDA(cudaMemsetAsync(d.x, 0xff, (size_t)A.dim()*sizeof(double), st));
+	if(A.bs == 1)
+		tri_syncfree_kernel<1,KIND,false><<<div_up(nrows, 256), 256, 0, st>>>(d, ticket, err);
+	else if(A.bs == 4) {
+		const long long nwarps = (nrows + 7)/8;
+		if(aligned32(d.xsrc))
+			tri_syncfree_kernel<4,KIND,true><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+		else
+			tri_syncfree_kernel<4,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+	}
+	else if(A.bs == 5) {
+		const long long nwarps = (nrows + 5)/6;
+		tri_syncfree_kernel<5,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+	}
+	else throw Error("triangular solve: unsupported block size " + std::to_string(A.bs));
+	B200_LAUNCHED();
+}
+
+void launch_tri_syncfree(const Mat& A, TriKind kind, const TriArgs& a, int *ticket, int *err,
+                         cudaStream_t st)
+{
+	if(a.x == a.rhs) throw Error("triangular solve: output aliases the right-hand side");
+	TriDev d;
+	d.part_ptr = a.part_ptr; d.part_col = a.part_col; d.part_diag = a.part_diag;
+	d.browptr = A.browptr; d.bcolind = A.bcolind; d.diagind = A.diagind;
+	d.vals = a.vals; d.dinv = a.dinv; d.rhs = a.rhs; d.rscale = a.rscale;
+	d.xsrc = a.x; d.x = a.x; d.rows = a.rows;
+	d.row_begin = a.row_begin; d.row_end = a.row_end; d.descending = a.descending ? 1 : 0;
+	ProfScope ps((kind == TRI_ILU_LOWER || kind == TRI_SGS_FWD) ? KC_TRI_LOWER : KC_TRI_UPPER, st);
+	switch(kind) {
+	case TRI_ILU_LOWER: launch_syncfree_kind<TRI_ILU_LOWER>(A, d, ticket, err, st); break;
+	case TRI_ILU_UPPER: launch_syncfree_kind<TRI_ILU_UPPER>(A, d, ticket, err, st); break;
+	case TRI_SGS_FWD: launch_syncfree_kind<TRI_SGS_FWD>(A, d, ticket, err, st); break;
+	case TRI_SGS_BWD: launch_syncfree_kind<TRI_SGS_BWD>(A, d, ticket, err, st); break;
+	default: throw Error("triangular solve: relaxation has no one-launch form");
+	}
+}
+
 // ------------------------------------------------------------------ Jacobi application
 
 template <int BS>

@@ -280,6 +280,10 @@ struct TriArgs {
 	const double *part_diag = nullptr;
 };
 void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t st);
+/// exact substitution over the level-sorted row list `a.rows` (all rows) in one launch; a.x must not
+/// alias a.rhs; *err is raised if a dependency never arrives (invalid ordering)
+void launch_tri_syncfree(const Mat& A, TriKind kind, const TriArgs& a, int *ticket, int *err,
+                         cudaStream_t st);
 void launch_jacobi_apply(const Mat& A, const double *dinv, const double *r, double *z,
                          cudaStream_t st);
 void launch_vec_scale_copy(long long n, const double *scale, const double *in, double *out,
@@ -334,6 +338,7 @@ struct Prec {
 	DevBuf<double> lev_r, lev_z;
 	cudaStream_t cap_stream = nullptr;
 	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
+	DevBuf<int> sync_flags;                           ///< {ticket, error} of the one-launch exact solves
 
 	int dim() const { return A->nbrows*A->bs; }
 };

@@ -544,7 +544,21 @@ void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st)
 		return;
 	}
 
-	// DAG wavefronts
+	// DAG wavefronts.  The backward substitutions walk the same levels in reverse, which is only a
+	// valid order when the pattern is structurally symmetric - the assumption the reference states
+	// at levelschedule.cpp:55-57 (and throws on); checked here as well.
+	{
+		DevBuf<int> d_bad;
+		d_bad.alloc(1);
+		B200_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+		symmetry_check_kernel<<<div_up(A.nnzb, 256), 256, 0, st>>>(A.nnzb, A.browptr, A.bcolind,
+		                                                          A.browind, d_bad);
+		B200_LAUNCHED();
+		int bad = 0;
+		B200_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		if(bad) throw Error("Faulty dependency list!");
+	}
 	DevBuf<int> level, changed, rows_in, level_sorted;
 	level.alloc(n);
 	changed.alloc(1);

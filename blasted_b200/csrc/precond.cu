@@ -231,6 +231,47 @@ static void run_level_graph(Prec& P, int slot, const double *r, double *z, Body 
 	B200_CUDA(cudaMemcpyAsync(z, P.lev_z, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 }
 
+/// Exact triangular solves: per-level launches replayed as a CUDA graph, or - for schedules of many
+/// narrow levels - one launch per triangle over the level-sorted rows (apply.cu::
+/// tri_syncfree_kernel).  Measured per level and triangle: ~4 us for a graph node whatever the
+/// level's size, ~2.8 us for the polled hand-over when a level is a few CTAs wide (C2, 2047 levels
+/// of 512 block rows: 16.5 -> 11.3 ms per apply) but 4.5-12 us when tens of thousands of rows poll
+/// at once (7-point 256^3: 6.9 vs 6.3 ms, 27-point: 27.6 vs 7.7 ms).  B200_LEVEL_GRAPH=1 /
+/// B200_LEVEL_ONE_LAUNCH=1 force either form (development).
+static bool one_launch_levels(Prec& P)
+{
+	static const bool force_graph = getenv("B200_LEVEL_GRAPH") != nullptr;
+	static const bool force_one = getenv("B200_LEVEL_ONE_LAUNCH") != nullptr;
+	if(force_graph || P.levels.mode != B200_LEVELS_DAG || !P.levels.level_rows.p) return false;
+	const double rows_per_level = (double)P.A->nbrows/std::max(P.levels.nlevels, 1);
+	if(!force_one && rows_per_level >= 1024.0) return false;
+	if(!P.sync_flags.p) {
+		P.sync_flags.alloc(2);
+		B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), P.stream));
+	}
+	return true;
+}
+
+static void exact_pair(Prec& P, TriKind lower, TriKind upper, TriArgs aL, TriArgs aU,
+                       const double *r, double *z)
+{
+	// lower: rhs r -> ytemp ; upper: rhs ytemp -> z, both over all rows in level order
+	const int n = P.A->nbrows;
+	aL.rows = aU.rows = P.levels.level_rows.p;
+	aL.row_begin = aU.row_begin = 0; aL.row_end = aU.row_end = n;
+	aL.rhs = r; aL.x = P.ytemp; aL.descending = false;
+	aU.rhs = P.ytemp; aU.x = z; aU.descending = true;
+	double *zz = z;
+	if(z == r) {                       // in-place call: the upper solve may not overwrite r early
+		if(!P.lev_z.p) { P.lev_r.alloc(P.A->dim()); P.lev_z.alloc(P.A->dim()); }
+		aU.x = zz = P.lev_z;
+	}
+	launch_tri_syncfree(*P.A, lower, aL, P.sync_flags.p, P.sync_flags.p + 1, P.stream);
+	launch_tri_syncfree(*P.A, upper, aU, P.sync_flags.p, P.sync_flags.p + 1, P.stream);
+	if(zz != z)
+		B200_CUDA(cudaMemcpyAsync(z, zz, P.A->dim()*sizeof(double), cudaMemcpyDeviceToDevice, P.stream));
+}
+
 static void level_sweep(Prec& P, TriKind kind, TriArgs a, bool backward)
 {
 	const Mat& A = *P.A;
@@ -314,7 +355,11 @@ void prec_apply(Prec& P, const double *r, double *z)
 	}
 	else if(type == B200_LEVEL_SGS) {
 		// Level_SGS::apply, solverops_levels_sgs.cpp:54-87,160-189
-		run_level_graph(P, 0, r, z, [&] {
+		if(one_launch_levels(P)) {
+			TriArgs a; a.vals = A.vals; a.dinv = P.dinv;
+			exact_pair(P, TRI_SGS_FWD, TRI_SGS_BWD, a, a, r, z);
+		}
+		else run_level_graph(P, 0, r, z, [&] {
 			TriArgs a; a.vals = A.vals; a.dinv = P.dinv;
 			a.rhs = P.lev_r; a.x = P.ytemp;
 			level_sweep(P, TRI_SGS_FWD, a, false);
@@ -341,7 +386,11 @@ void prec_apply(Prec& P, const double *r, double *z)
 			// triangular solves of the sequential variants
 			if(!P.uses_levels && P.s.apply_inittype == B200_INIT_A_NONE)
 				throw Error(" scalar_ilu0_apply: Invalid init type!");
-			run_level_graph(P, 0, r, z, [&] {
+			if(one_launch_levels(P)) {
+				aL.rscale = scale; aU.rscale = nullptr;
+				exact_pair(P, TRI_ILU_LOWER, TRI_ILU_UPPER, aL, aU, r, z);
+			}
+			else run_level_graph(P, 0, r, z, [&] {
 				aL.rhs = P.lev_r; aL.rscale = scale; aL.x = P.ytemp;
 				level_sweep(P, TRI_ILU_LOWER, aL, false);
 				aU.rhs = P.ytemp; aU.rscale = nullptr; aU.x = P.lev_z;
