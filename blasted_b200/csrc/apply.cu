@@ -360,6 +360,7 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
+	constexpr int DK = (BS == 1) ? 8 : 3;       // dependencies held in registers and polled together
 	__shared__ int s_cta;
 	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
 	__syncthreads();
@@ -369,7 +370,7 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 	const long long t = warp*GPW + g;
 	const int nrows = a.row_end - a.row_begin;
 	const bool valid = (g < GPW) && (t < nrows);
-	int row = 0, k = 0, je = 0;
+	int row = 0, cbase = 0, je = 0;
 	const int *cols = a.bcolind;
 	double acc = 0, rhs = 0;
 	double dr[BS];
@@ -379,13 +380,37 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
 		row = a.rows ? __ldg(a.rows + idx) : idx;
 		if(BS == 1 && a.part_ptr) {
-			k = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
+			cbase = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
 			cols = a.part_col;
 		} else {
 			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
 			const int d = __ldg(a.diagind + row);
-			part_range<KIND>(s, d, e, k, je);
+			part_range<KIND>(s, d, e, cbase, je);
 		}
+	}
+	// the current chunk of up to DK dependencies: column indices and matrix entries in registers,
+	// loaded before any waiting so that the hand-over from one level to the next costs L2 round
+	// trips only (polls of x), never a DRAM miss on the row's own data
+	int pc[DK];
+	double pv[DK][BS];
+	int nb = 0, adv = 0;
+	auto load_chunk = [&]() {
+		nb = min(DK, je - cbase);
+		adv = 0;
+#pragma unroll
+		for(int q = 0; q < DK; q++) {
+			pc[q] = 0;
+#pragma unroll
+			for(int c = 0; c < BS; c++) pv[q][c] = 0;
+			if(q < nb) {
+				pc[q] = __ldg(cols + cbase + q);
+				if(BS == 1) pv[q][0] = __ldg(a.vals + cbase + q);
+				else BlkIO<BS>::template load_row<false>(a.vals + (size_t)(cbase + q)*BS2, r, pv[q]);
+			}
+		}
+	};
+	load_chunk();
+	if(valid) {
 		rhs = __ldg(a.rhs + (size_t)row*BS + r);
 		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
 		if(BS > 1 && KIND != TRI_ILU_LOWER)
@@ -399,53 +424,62 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 	bool stored = !valid;
 	int spins = 0;
 	while(true) {
-		if(!stored) {
-			// consume, in column order, every dependency that has been published.  The next DK
-			// dependencies are polled together (one L2 round trip, not DK) and the ready prefix
-			// is accumulated.
-			constexpr int DK = (BS == 1) ? 8 : 3;
-			while(k < je) {
-				const int nb = min(DK, je - k);
-				int col[DK];
-				double xv[DK][BS];
+		// While a warp waits, only its first unfinished lane polls (its next dependency): the rows
+		// of a warp are level-sorted, so that lane becomes ready first, and tens of thousands of
+		// waiting rows polling all their dependencies saturate L2 and stretch every hand-over.
+		const unsigned waiting = __ballot_sync(0xffffffffu, !stored && cbase < je);
+		if(waiting) {
+			const int leader = __ffs(waiting) - 1;
+			int ready = 1;
+			if(lane == leader) {
+				int col = pc[0];
 #pragma unroll
-				for(int q = 0; q < DK; q++) col[q] = (q < nb) ? __ldg(cols + k + q) : 0;
-#pragma unroll
-				for(int q = 0; q < DK; q++) {
-					if(q < nb) {
-						if(BS == 4 && VEC)
-							ld256_cg_ordered(a.xsrc + (size_t)col[q]*BS, xv[q][0], xv[q][1], xv[q][2], xv[q][3]);
-						else {
-#pragma unroll
-							for(int c = 0; c < BS; c++) xv[q][c] = ld_poll(a.xsrc + (size_t)col[q]*BS + c);
-						}
-					} else {
-#pragma unroll
-						for(int c = 0; c < BS; c++) xv[q][c] = 0;
-					}
+				for(int q = 1; q < DK; q++) if(q == adv) col = pc[q];
+				ready = !is_unset(ld_poll(a.xsrc + (size_t)col*BS + ((BS > 1) ? r : 0)));
+			}
+			ready = __shfl_sync(0xffffffffu, ready, leader);
+			const bool somebody_done = __any_sync(0xffffffffu, !stored && cbase >= je);
+			if(!ready && !somebody_done) {
+				__nanosleep(32);
+				if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
+					if(spins > (1 << 22) || *((volatile int*)err)) { *err = 1; cbase = je; }
 				}
-				int adv = 0;
-#pragma unroll
-				for(int q = 0; q < DK; q++) {
-					bool unset = false;
-#pragma unroll
-					for(int c = 0; c < BS; c++) unset |= is_unset(xv[q][c]);
-					if(q < nb && adv == q && !unset) {
-						if(BS == 1) acc = fma(__ldg(a.vals + k + q), xv[q][0], acc);
-						else {
-							double av[BS];
-							BlkIO<BS>::template load_row<false>(a.vals + (size_t)(k + q)*BS2, r, av);
-#pragma unroll
-							for(int c = 0; c < BS; c++) acc = fma(av[c], xv[q][c], acc);
-						}
-						adv++;
-					}
-				}
-				k += adv;
-				if(adv < nb) break;
+				continue;
 			}
 		}
-		const bool fin = !stored && k == je;
+		if(!stored && cbase < je) {
+			// poll the rest of the chunk together and consume the ready prefix in column order
+			double xv[DK][BS];
+#pragma unroll
+			for(int q = 0; q < DK; q++) {
+#pragma unroll
+				for(int c = 0; c < BS; c++) xv[q][c] = 0;
+				if(q >= adv && q < nb) {
+					if(BS == 4 && VEC)
+						ld256_cg_ordered(a.xsrc + (size_t)pc[q]*BS, xv[q][0], xv[q][1], xv[q][2], xv[q][3]);
+					else {
+#pragma unroll
+						for(int c = 0; c < BS; c++) xv[q][c] = ld_poll(a.xsrc + (size_t)pc[q]*BS + c);
+					}
+				}
+			}
+#pragma unroll
+			for(int q = 0; q < DK; q++) {
+				bool unset = false;
+#pragma unroll
+				for(int c = 0; c < BS; c++) unset |= is_unset(xv[q][c]);
+				if(q == adv && q < nb && !unset) {
+#pragma unroll
+					for(int c = 0; c < BS; c++) acc = fma(pv[q][c], xv[q][c], acc);
+					adv++;
+				}
+			}
+			if(adv == nb) {
+				cbase += nb;
+				if(cbase < je) load_chunk();
+			}
+		}
+		const bool fin = !stored && cbase >= je;
 		// epilogue with the whole warp converged (the block forms exchange values by shuffles)
 		double out;
 		if(KIND == TRI_ILU_LOWER) out = rhs - acc;
@@ -466,12 +500,6 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 			stored = true;
 		}
 		if(__all_sync(0xffffffffu, stored)) break;
-		if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
-			if(spins > (1 << 22) || *((volatile int*)err)) {
-				*err = 1;
-				k = je;                               // stop waiting; the result is flagged invalid
-			}
-		}
 	}
 }
 

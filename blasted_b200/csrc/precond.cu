@@ -231,20 +231,16 @@ static void run_level_graph(Prec& P, int slot, const double *r, double *z, Body 
 	B200_CUDA(cudaMemcpyAsync(z, P.lev_z, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 }
 
-/// Exact triangular solves: per-level launches replayed as a CUDA graph, or - for schedules of many
-/// narrow levels - one launch per triangle over the level-sorted rows (apply.cu::
-/// tri_syncfree_kernel).  Measured per level and triangle: ~4 us for a graph node whatever the
-/// level's size, ~2.8 us for the polled hand-over when a level is a few CTAs wide (C2, 2047 levels
-/// of 512 block rows: 16.5 -> 11.3 ms per apply) but 4.5-12 us when tens of thousands of rows poll
-/// at once (7-point 256^3: 6.9 vs 6.3 ms, 27-point: 27.6 vs 7.7 ms).  B200_LEVEL_GRAPH=1 /
-/// B200_LEVEL_ONE_LAUNCH=1 force either form (development).
+/// Exact triangular solves over a DAG schedule run as ONE launch per triangle over the level-sorted
+/// rows (apply.cu::tri_syncfree_kernel); the reference-identical contiguous schedule, whose levels
+/// are row ranges, keeps per-level launches replayed as a CUDA graph.  Measured per apply (L + U),
+/// graph -> one launch: 7-point 256^3 (766 levels) 6.3 -> 3.5 ms, C2 (2047 levels of 512 block
+/// rows) 16.5 -> 5.3 ms, bs=5 96^3 (286 levels) 3.25 -> 1.1 ms, 27-point 160^3 7.7 -> 7.6 ms;
+/// results are bit-identical.  B200_LEVEL_GRAPH=1 forces the graph form (development).
 static bool one_launch_levels(Prec& P)
 {
 	static const bool force_graph = getenv("B200_LEVEL_GRAPH") != nullptr;
-	static const bool force_one = getenv("B200_LEVEL_ONE_LAUNCH") != nullptr;
 	if(force_graph || P.levels.mode != B200_LEVELS_DAG || !P.levels.level_rows.p) return false;
-	const double rows_per_level = (double)P.A->nbrows/std::max(P.levels.nlevels, 1);
-	if(!force_one && rows_per_level >= 1024.0) return false;
 	if(!P.sync_flags.p) {
 		P.sync_flags.alloc(2);
 		B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), P.stream));
