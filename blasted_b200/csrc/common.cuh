@@ -208,6 +208,10 @@ void scalar_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, i
                       ScalarFactor& F, cudaStream_t st);
 void scalar_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
                        int *d_changed, bool all_upper, cudaStream_t st);
+/// exact factorisation in one launch over the level-sorted rows; rowdone: nbrows ints of scratch,
+/// flags: {ticket, error}
+void scalar_ilu0_exact(const Mat& A, const IluPattern& pl, const int *level_rows, const double *scale,
+                       ScalarFactor& F, int *rowdone, int *flags, cudaStream_t st);
 double scalar_ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale,
                             const ScalarFactor& F, double *d_scratch, cudaStream_t st);
 /// out[entry] for every stored entry, in the reference's iluvals ordering
@@ -339,6 +343,7 @@ struct Prec {
 	cudaStream_t cap_stream = nullptr;
 	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
 	DevBuf<int> sync_flags;                           ///< {ticket, error} of the one-launch exact solves
+	DevBuf<int> rowdone;                              ///< per-row flags of the one-launch exact factorisation
 
 	int dim() const { return A->nbrows*A->bs; }
 };

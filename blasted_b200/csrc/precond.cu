@@ -41,6 +41,8 @@ static double elapsed(Prec& P)
 
 // ------------------------------------------------------------------ compute
 
+static bool exact_in_one_launch(Prec& P);
+
 void prec_compute(Prec& P, double precinfo[6])
 {
 	Mat& A = *P.A;
@@ -86,7 +88,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			if(P.s.scale) P.scale.alloc(A.dim());
 			P.flag.alloc(1);
 			// levels first, as Async_Level_*::compute does (solverops_levels_ilu0.cpp:52-56,139-145)
-			if(P.uses_levels || !P.threadedapply)
+			if(P.uses_levels || !P.threadedapply || !P.threadedfactor)
 				build_levels(A, P.levels, P.uses_levels ? P.s.level_mode : B200_LEVELS_DAG, st);
 			build_ilu_pattern(A, P.pl, st);
 			// the reference copies A into iluvals at allocation (solverops_ilu0.cpp:160-164,333-337);
@@ -138,6 +140,12 @@ void prec_compute(Prec& P, double precinfo[6])
 		if(P.threadedfactor) {
 			for(int sw = 0; sw < P.s.nbuildsweeps; sw++) sweep(sw, nullptr);
 			P.factor_sweeps_done = P.s.nbuildsweeps;
+		}
+		else if(P.s.nbuildsweeps > 0 && scalar && exact_in_one_launch(P)) {
+			// exact factorisation: one launch over the level-sorted rows (scalar_ilu.cu)
+			if(!P.rowdone.p) P.rowdone.alloc(std::max(A.nbrows, 1));
+			scalar_ilu0_exact(A, P.pl, P.levels.level_rows, scale, P.sf, P.rowdone, P.sync_flags, st);
+			P.factor_sweeps_done = 1;
 		}
 		else if(P.s.nbuildsweeps > 0) {
 			// exact factorisation: iterate to the bitwise fixed point
@@ -246,6 +254,21 @@ static bool one_launch_levels(Prec& P)
 		B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), P.stream));
 	}
 	return true;
+}
+
+/// The exact scalar factorisation has a one-launch form too (scalar_ilu.cu::scalar_exact_kernel).
+/// Its cost is levels x (one row's dependent load chain, ~20 us on a 7-point row), the sweeps' cost
+/// is (sweeps to the bitwise fixed point) x (sweep time): measured 7-point 256^3 34.7 -> 15.4 ms,
+/// 27-point 160^3 865 -> 173 ms, but 7-point 128^3 4.8 -> 6.7 ms - so it is used from a million
+/// rows up, where the number of sweeps is what hurts.  B200_EXACT_SWEEPS=1 / B200_EXACT_ONE_LAUNCH=1
+/// force either form (development, tests).
+static bool exact_in_one_launch(Prec& P)
+{
+	static const bool force_sweeps = getenv("B200_EXACT_SWEEPS") != nullptr;
+	static const bool force_one = getenv("B200_EXACT_ONE_LAUNCH") != nullptr;
+	if(force_sweeps) return false;
+	if(!force_one && P.A->nbrows < (1 << 20)) return false;
+	return one_launch_levels(P);
 }
 
 static void exact_pair(Prec& P, TriKind lower, TriKind upper, TriArgs aL, TriArgs aU,

@@ -179,6 +179,123 @@ scalar_gather_kernel(const long long nlower, const long long nupper, const int4 
 	}
 }
 
+
+// ------------------------------------------------------------------ exact factorisation, one launch
+
+__device__ __forceinline__ int ld_poll_int(const int *p)
+{
+	int v;
+	asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+/// Exact ILU(0) in ONE launch: one thread per row, rows taken in level-sorted order (CTA positions
+/// from a ticket counter, as apply.cu::tri_syncfree_kernel), a row waits until every row named by
+/// its lower part has raised its flag and then computes its entries in storage order - exactly the
+/// sequential pass of the reference's kernel (tests/solverops/async_ilu_convergence.cpp:462-490),
+/// with the per-entry arithmetic of the sweep kernels above, so the result is bit-identical to the
+/// fixed point the sweeps iterate to.  While a warp waits only its first unfinished lane polls.
+template <bool SCALE>
+__global__ void __launch_bounds__(256)
+scalar_exact_kernel(const int nrows, const int *__restrict__ rows, const int *__restrict__ lptr,
+                    const int *__restrict__ uptr, const int *__restrict__ lcol,
+                    const int4 *__restrict__ lmeta, const int4 *__restrict__ uall,
+                    const int *__restrict__ browind, const int *__restrict__ bcolind,
+                    const double *__restrict__ avals, const double *__restrict__ scale,
+                    const int2 *__restrict__ spairs, double *lval, double *uval, double *udiag,
+                    int *rowdone, int *__restrict__ ticket, int *__restrict__ err)
+{
+	__shared__ int s_cta;
+	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const long long t = (long long)s_cta*blockDim.x + threadIdx.x;
+	const bool valid = t < nrows;
+	int row = 0, ls = 0, le = 0, us = 0, ue = 0;
+	if(valid) {
+		row = __ldg(rows + t);
+		ls = __ldg(lptr + row); le = __ldg(lptr + row + 1);
+		us = __ldg(uptr + row) + row; ue = __ldg(uptr + row + 1) + row + 1;
+	}
+	int kdep = ls;
+	bool done = !valid;
+	int spins = 0;
+	while(true) {
+		const unsigned waiting = __ballot_sync(0xffffffffu, !done);
+		if(!waiting) break;
+		const int leader = __ffs(waiting) - 1;
+		if(lane == leader)
+			while(kdep < le && ld_poll_int(rowdone + __ldg(lcol + kdep)) != 0) kdep++;
+		const int go = __shfl_sync(0xffffffffu, (int)(kdep == le), leader);
+		if(!go) {
+			__nanosleep(64);
+			if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
+				if(spins > (1 << 22) || *((volatile int*)err)) { *err = 1; kdep = le; }
+			}
+			continue;
+		}
+		if(!done) {
+			while(kdep < le && ld_poll_int(rowdone + __ldg(lcol + kdep)) != 0) kdep++;
+			if(kdep == le) {
+				__threadfence();
+				for(int i = ls; i < le; i++) {
+					const int4 m = __ldg(lmeta + i);                 // {entry, col, ps, pe}
+					double sum = __ldg(avals + m.x);
+					if(SCALE) {
+						sum *= __ldg(scale + __ldg(browind + m.x));
+						sum *= __ldg(scale + m.y);
+					}
+					for(int k = m.z; k < m.w; k++) {
+						const int2 pr = __ldg(spairs + k);
+						sum = fma(-ld_iter(lval + pr.x), ld_iter(uval + pr.y), sum);
+					}
+					lval[i] = sum/ld_iter(udiag + m.y);
+				}
+				for(int i = us; i < ue; i++) {
+					const int4 m = __ldg(uall + i);                  // {entry, ps, pe, dest}
+					double sum = __ldg(avals + m.x);
+					if(SCALE) {
+						sum *= __ldg(scale + __ldg(browind + m.x));
+						sum *= __ldg(scale + __ldg(bcolind + m.x));
+					}
+					for(int k = m.y; k < m.z; k++) {
+						const int2 pr = __ldg(spairs + k);
+						sum = fma(-ld_iter(lval + pr.x), ld_iter(uval + pr.y), sum);
+					}
+					if(m.w < 0) udiag[~m.w] = sum; else uval[m.w] = sum;
+				}
+				__threadfence();
+				*((volatile int*)(rowdone + row)) = 1;
+				done = true;
+			}
+		}
+	}
+}
+
+}  // namespace
+
+void scalar_ilu0_exact(const Mat& A, const IluPattern& pl, const int *level_rows, const double *scale,
+                       ScalarFactor& F, int *rowdone, int *flags, cudaStream_t st)
+{
+	const int n = A.nbrows;
+	if(n == 0) return;
+	ProfScope ps(KC_FACTOR_LOWER, st);
+	B200_CUDA(cudaMemsetAsync(rowdone, 0, (size_t)n*sizeof(int), st));
+	B200_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));                // ticket
+	const int grid = div_up(n, 256);
+	if(scale)
+		scalar_exact_kernel<true><<<grid, 256, 0, st>>>(n, level_rows, pl.lptr, pl.uptr, pl.lcol,
+			pl.slmeta, pl.suall, A.browind, A.bcolind, A.vals, scale, pl.spairs, F.lval.p, F.uval.p,
+			F.udiag.p, rowdone, flags, flags + 1);
+	else
+		scalar_exact_kernel<false><<<grid, 256, 0, st>>>(n, level_rows, pl.lptr, pl.uptr, pl.lcol,
+			pl.slmeta, pl.suall, A.browind, A.bcolind, A.vals, scale, pl.spairs, F.lval.p, F.uval.p,
+			F.udiag.p, rowdone, flags, flags + 1);
+	B200_LAUNCHED();
+}
+
+namespace {
+
 template <int MODE>
 void run_lower(const Mat& A, const IluPattern& pl, const double *scale, const ScalarFactor& F,
                double *res, int *changed, cudaStream_t st)

@@ -195,3 +195,38 @@ def test_synthetic_exact_and_async(mk):
     assert relerr(p.factor(), exact) < TOL
     r = np.random.default_rng(SEED).standard_normal(m.dim)
     assert relerr(p.apply(r), O.ilu0_apply(m, exact, None, 1, "init_zero", r)) < TOL
+
+
+def test_one_launch_exact_factorisation_small_cases():
+    """The one-launch exact scalar factorisation is only selected from a million rows up; force it
+    on the fixtures (fresh process: the switch is read once) and compare with the oracle."""
+    import os, subprocess, sys
+    code = r'''
+import sys, os
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+import blasted_b200 as bb
+from blasted_b200.solverfactory import SOLVER_TYPES
+from oracle import orc
+from util import case, relerr
+for key, scale in (("2dcyl1_csr", False), ("2dcyl1_csr", True), ("msc00726_csr", True)):
+    m = case(key)
+    sv = orc().scaling_vector(m) if scale else None
+    exact = orc().exact_ilu0(m, sv)
+    p = bb.SRFactory().create_preconditioner(bb.SRMatrixView(m), bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["sfilu0"], bs=1, scale=scale, nbuildsweeps=1))
+    p.compute()
+    assert relerr(p.factor(), exact) < 1e-12, key
+    r = np.cos(np.arange(m.dim))
+    q = bb.SRFactory().create_preconditioner(bb.SRMatrixView(m), bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["seqilu0"], bs=1, scale=scale, nbuildsweeps=1))
+    q.compute()
+    assert np.array_equal(q.factor(), p.factor())
+    assert np.isfinite(q.apply(r)).all()
+print("ok")
+'''
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = dict(os.environ, B200_EXACT_ONE_LAUNCH="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
