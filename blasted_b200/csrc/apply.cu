@@ -354,13 +354,12 @@ __device__ __forceinline__ bool is_unset(const double v)
 /// changes: same per-row arithmetic in the same column order as tri_scalar/tri_block_kernel, one
 /// final store per value.  The spin is bounded: past the cap a warp raises *err and stops waiting
 /// (a dependency pointing forward in the list - a pattern the level builder should have refused).
-template <int BS, int KIND, bool VEC>
+template <int BS, int KIND, bool VEC, int DK>    // DK: dependencies held in registers and polled together
 __global__ void __launch_bounds__(256)
 tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ err)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
-	constexpr int DK = (BS == 1) ? 8 : 3;       // dependencies held in registers and polled together
 	__shared__ int s_cta;
 	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
 	__syncthreads();
@@ -510,18 +509,23 @@ static void launch_syncfree_kind(const Mat& A, const TriDev& d, int *ticket, int
 	if(nrows <= 0) return;
 	B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(int), st));
 	B200_CUDA(cudaMemsetAsync(d.x, 0xff, (size_t)A.dim()*sizeof(double), st));
-	if(A.bs == 1)
-		tri_syncfree_kernel<1,KIND,false><<<div_up(nrows, 256), 256, 0, st>>>(d, ticket, err);
+	if(A.bs == 1) {
+		// row parts of up to 8 / up to 16 entries in one chunk (7-point: 3, 27-point: 13)
+		if(A.avg_row_len <= 17.0)
+			tri_syncfree_kernel<1,KIND,false,8><<<div_up(nrows, 256), 256, 0, st>>>(d, ticket, err);
+		else
+			tri_syncfree_kernel<1,KIND,false,16><<<div_up(nrows, 256), 256, 0, st>>>(d, ticket, err);
+	}
 	else if(A.bs == 4) {
 		const long long nwarps = (nrows + 7)/8;
 		if(aligned32(d.xsrc))
-			tri_syncfree_kernel<4,KIND,true><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+			tri_syncfree_kernel<4,KIND,true,3><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
 		else
-			tri_syncfree_kernel<4,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+			tri_syncfree_kernel<4,KIND,false,3><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
 	}
 	else if(A.bs == 5) {
 		const long long nwarps = (nrows + 5)/6;
-		tri_syncfree_kernel<5,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
+		tri_syncfree_kernel<5,KIND,false,3><<<div_up(nwarps*32, 256), 256, 0, st>>>(d, ticket, err);
 	}
 	else throw Error("triangular solve: unsupported block size " + std::to_string(A.bs));
 	B200_LAUNCHED();

@@ -243,7 +243,7 @@ static void run_level_graph(Prec& P, int slot, const double *r, double *z, Body 
 /// rows (apply.cu::tri_syncfree_kernel); the reference-identical contiguous schedule, whose levels
 /// are row ranges, keeps per-level launches replayed as a CUDA graph.  Measured per apply (L + U),
 /// graph -> one launch: 7-point 256^3 (766 levels) 6.3 -> 3.5 ms, C2 (2047 levels of 512 block
-/// rows) 16.5 -> 5.3 ms, bs=5 96^3 (286 levels) 3.25 -> 1.1 ms, 27-point 160^3 7.7 -> 7.6 ms;
+/// rows) 16.5 -> 5.3 ms, bs=5 96^3 (286 levels) 3.25 -> 1.1 ms, 27-point 160^3 7.7 -> 6.1 ms;
 /// results are bit-identical.  B200_LEVEL_GRAPH=1 forces the graph form (development).
 static bool one_launch_levels(Prec& P)
 {
