@@ -671,9 +671,24 @@ invert_blocks_kernel(const int nbrows, const double *src, const int *__restrict_
 	const bool active = (g < GPW) && (rowl < nbrows);
 	double d[BS2], e[BS], x[BS];
 	size_t spos = 0;
+	if(active) spos = positions ? (size_t)__ldg(positions + rowl) : (size_t)rowl;
+	if(BS == 4) {
+		// four 256-bit loads of the whole block per lane (measured faster than the gather below)
+		if(active) BlkIO<BS>::template load_full<true>(src + spos*BS2, d);
+	} else {
+		// 64-bit loads: every lane reads its own row (5 requests, not 25) and the group assembles
+		// the block by shuffles, as the fused upper launch does (bs=5 96^3: 0.160 -> 0.142 ms)
+		double rowv[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) rowv[c] = 0;
+		if(active) BlkIO<BS>::template load_row<true>(src + spos*BS2, r, rowv);
+#pragma unroll
+		for(int c = 0; c < BS; c++)
+#pragma unroll
+			for(int m = 0; m < BS; m++)
+				d[c*BS+m] = __shfl_sync(0xffffffffu, rowv[c], min(g*BS + m, 31));
+	}
 	if(active) {
-		spos = positions ? (size_t)__ldg(positions + rowl) : (size_t)rowl;
-		BlkIO<BS>::template load_full<true>(src + spos*BS2, d);
 #pragma unroll
 		for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
 		solve_right<BS>(d, e, x);          // row r of the inverse
