@@ -200,6 +200,48 @@ __device__ __forceinline__ void load_seg(const double *x, double (&xv)[BS])
 
 inline bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31) == 0; }
 
+// ------------------------------------------------------------------ cooperative block inverse
+
+/// Inverse of a bs x bs block held one row per lane (lane base + m holds row m in a[]), by
+/// Gauss-Jordan elimination with partial pivoting across the group: pivot search and the pivot
+/// row travel by shuffles, every lane eliminates in its own row.  10 (bs 5) / 8 (bs 4) doubles of
+/// state per lane instead of the bs^2 + 2 bs of the redundant per-lane elimination (solve_right),
+/// which is what lets the factor launches refresh U_ii^-1 themselves without losing a resident CTA.
+/// On return `inv` holds row `prow` of the inverse (rows end up where their pivots were found).
+/// Must be called by all lanes of the warp; `base` = first lane of the caller's group.
+template <int BS>
+__device__ __forceinline__ void group_inverse(double (&a)[BS], double (&inv)[BS], const int base,
+                                              const int r, int& prow)
+{
+#pragma unroll
+	for(int c = 0; c < BS; c++) inv[c] = (c == r) ? 1.0 : 0.0;
+	prow = -1;
+#pragma unroll
+	for(int k = 0; k < BS; k++) {
+		// pivot: largest |a_mk| among the rows not used yet (lowest row on ties, same on every lane)
+		const double mine = (prow < 0) ? fabs(a[k]) : -1.0;
+		double best = -2.0;
+		int bl = 0;
+#pragma unroll
+		for(int m = 0; m < BS; m++) {
+			const double v = __shfl_sync(0xffffffffu, mine, min(base + m, 31));
+			if(v > best) { best = v; bl = m; }
+		}
+		const int src = min(base + bl, 31);
+		const double rinv = 1.0/__shfl_sync(0xffffffffu, a[k], src);
+		const bool is_pivot = (r == bl);
+		const double f = a[k]*rinv;
+#pragma unroll
+		for(int c = 0; c < BS; c++) {
+			const double pa = __shfl_sync(0xffffffffu, a[c], src);
+			const double pi = __shfl_sync(0xffffffffu, inv[c], src);
+			if(is_pivot) { a[c] = pa*rinv; inv[c] = pi*rinv; }
+			else { a[c] = fma(-f, pa, a[c]); inv[c] = fma(-f, pi, inv[c]); }
+		}
+		if(is_pivot) prow = k;
+	}
+}
+
 // ------------------------------------------------------------------ dense solve in registers
 
 /// Solves x * D = s for the row vector x, with D handed over as d[c*BS + m] = D(m,c).

@@ -27,7 +27,8 @@
  * block ("entry-parallel", packed per-phase work lists from pattern.cu), lane r owns row r of the
  * block in registers; products stream the partner's rows through warp shuffles
  * (blockops.cuh::group_mul_sub); U_jj^-1 comes from the compact array `dinv`, which the upper launch
- * refreshes with a register-resident bs x bs elimination with partial pivoting (solve_right).
+ * refreshes with a bs x bs Gauss-Jordan elimination with partial pivoting shared by the bs lanes of
+ * the group (blockops.cuh::group_inverse).
  * All of it is HBM/L2-bound; algorithmic bytes per launch are listed in DESIGN.md section 3.
  */
 #include "common.cuh"
@@ -403,7 +404,7 @@ block_ilu0_lower_simple_kernel(const long long nlower, const int2 *__restrict__ 
 }
 
 template <int BS, bool SCALE, bool FUSE_INV>
-__global__ void __launch_bounds__(256, (FUSE_INV ? 3 : 4))
+__global__ void __launch_bounds__(256, 4)
 block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
                         const int *__restrict__ browind, const int *__restrict__ bcolind,
                         const double *__restrict__ avals, const int2 *__restrict__ pairs,
@@ -469,18 +470,10 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 		// a diagonal entry refreshes the compact inverse: every lane of the group gathers the whole
 		// new block (row m lives in lane m) and solves for its own row of the inverse
 		if(FUSE_INV && __any_sync(0xffffffffu, isdiag)) {
-			double d[BS2], e[BS], x[BS];
-#pragma unroll
-			for(int c = 0; c < BS; c++)
-#pragma unroll
-				for(int m = 0; m < BS; m++)
-					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], min(g*BS + m, 31));
-			if(isdiag) {
-#pragma unroll
-				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
-				solve_right<BS>(d, e, x);
-				BlkIO<BS>::store_row(dinv + (size_t)meta.w*BS2, r, x);
-			}
+			double x[BS];
+			int prow;
+			group_inverse<BS>(sum, x, g*BS, r, prow);
+			if(isdiag) BlkIO<BS>::store_row(dinv + (size_t)meta.w*BS2, prow, x);
 		}
 		meta = metan;
 		t = tn;
@@ -562,10 +555,12 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 	}
 	if(nup > 0) {
 		ProfScope ps(KC_FACTOR_UPPER, st);
-		// bs = 4: the diagonal entries refresh U_ii^-1 inside this launch; bs = 5: the 5x5 pivoted
-		// elimination would cost the launch ~25 registers per thread (occupancy), so the inverses
-		// are refreshed by a separate pass over the N diagonal blocks
-		constexpr bool FUSE = (BS <= 4);
+		// the diagonal entries refresh U_ii^-1 inside this launch by the cooperative Gauss-Jordan
+		// of blockops.cuh::group_inverse (one row per lane: 64 registers, 4 CTAs/SM).  The
+		// redundant per-lane elimination it replaced cost bs = 4 a resident CTA (80 registers,
+		// 0.173 -> 0.165 ms on C2) and forced bs = 5 into a separate pass over the diagonal
+		// blocks (0.441 -> 0.378 ms on 96^3).
+		constexpr bool FUSE = true;
 		if(scale) {
 			auto k = block_ilu0_upper_kernel<BS,true,FUSE>;
 			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
@@ -669,33 +664,20 @@ invert_blocks_kernel(const int nbrows, const double *src, const int *__restrict_
 	const int g = lane / BS, r = lane - g*BS;
 	const long long rowl = warp*GPW + g;
 	const bool active = (g < GPW) && (rowl < nbrows);
-	double d[BS2], e[BS], x[BS];
 	size_t spos = 0;
 	if(active) spos = positions ? (size_t)__ldg(positions + rowl) : (size_t)rowl;
-	if(BS == 4) {
-		// four 256-bit loads of the whole block per lane (measured faster than the gather below)
-		if(active) BlkIO<BS>::template load_full<true>(src + spos*BS2, d);
-	} else {
-		// 64-bit loads: every lane reads its own row (5 requests, not 25) and the group assembles
-		// the block by shuffles, as the fused upper launch does (bs=5 96^3: 0.160 -> 0.142 ms)
-		double rowv[BS];
+	// every lane reads its own row of the block; the group inverts it cooperatively
+	// (blockops.cuh::group_inverse) and each lane ends up with the row of the inverse whose pivot
+	// its row supplied
+	double rowv[BS], x[BS];
+	int prow = 0;
 #pragma unroll
-		for(int c = 0; c < BS; c++) rowv[c] = 0;
-		if(active) BlkIO<BS>::template load_row<true>(src + spos*BS2, r, rowv);
-#pragma unroll
-		for(int c = 0; c < BS; c++)
-#pragma unroll
-			for(int m = 0; m < BS; m++)
-				d[c*BS+m] = __shfl_sync(0xffffffffu, rowv[c], min(g*BS + m, 31));
-	}
-	if(active) {
-#pragma unroll
-		for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
-		solve_right<BS>(d, e, x);          // row r of the inverse
-	}
+	for(int c = 0; c < BS; c++) rowv[c] = (c == r) ? 1.0 : 0.0;     // idle groups invert an identity
+	if(active) BlkIO<BS>::template load_row<true>(src + spos*BS2, r, rowv);
+	group_inverse<BS>(rowv, x, g*BS, r, prow);
 	__syncwarp();                          // all lanes have read the block before anyone overwrites it
 	if(active)
-		BlkIO<BS>::store_row(dst + (dst_compact ? (size_t)rowl : spos)*BS2, r, x);
+		BlkIO<BS>::store_row(dst + (dst_compact ? (size_t)rowl : spos)*BS2, prow, x);
 }
 
 __global__ void invert_scalars_kernel(const int n, const double *__restrict__ src,
