@@ -194,7 +194,7 @@ def run_reference(args):
                              "sample": f"full C2 step ({NBUILD} factor sweeps + {NAPPLY} apply sweep "
                                        f"pairs) x {args.steps} on the host cores"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(m, cells):
@@ -374,7 +374,7 @@ def run_b200(args):
             "algorithmic_bytes_per_step": by["step"],
             "reference_algorithm_bytes_per_step": ref_by["step"],
             "frac_of_peak_whole_step": value/world/peak}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -420,7 +420,28 @@ def run_fgmres(n, rank, world, dist):
             "time_to_solve_ms": best, "factor_included": True, "max_abs_error": err}
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: everything libraries print there while the bench runs
+    (NCCL's version banner under NCCL_DEBUG=VERSION, for one) is sent to stderr instead."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

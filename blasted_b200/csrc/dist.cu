@@ -222,6 +222,7 @@ int b200_comm_create(const char id[128], int rank, int world, b200_comm **out)
 		std::memcpy(u.internal, id, 128);
 		b200_comm *h = new b200_comm;
 		h->c.rank = rank; h->c.world = world;
+		if(world == 1) { *out = h; return; }          // a single subdomain never communicates
 		ncclResult_t r = g_nccl.CommInitRank(&h->c.comm, world, u, rank);
 		if(r != ncclSuccess) { delete h; throw Error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
 		*out = h;
