@@ -201,6 +201,7 @@ void gather_split_values(const IluPattern& pl, const double *vals, double *lval,
 /// Values of the scalar ILU(0) factor in split form (see IluPattern)
 struct ScalarFactor {
 	DevBuf<double> lval, uval, udiag;
+	DevBuf<double> alow, aupw;   ///< (scaled) entries of A in lower-list / upper-work-list order
 };
 
 // scalar_ilu.cu
