@@ -72,6 +72,74 @@ bsr_spmv_kernel(const int nbrows, const int *__restrict__ browptr, const int *__
 	else z[o] = acc;
 }
 
+/// Persistent, software-pipelined form for bs = 4 (the same idea as apply.cu::tri_block_pipe_kernel):
+/// with five blocks per row the chain  row pointers -> column indices -> x segments  bounds the
+/// one-shot kernel, so every group keeps the row pointers of its row after next and the first PK
+/// column indices of its next row in registers and requests all loads of the current row at once.
+/// Accumulation stays in column order (deterministic, identical to the one-shot kernel).
+template <bool G3>
+__global__ void __launch_bounds__(256, 4)
+bsr4_spmv_pipe_kernel(const int nbrows, const int *__restrict__ browptr,
+                      const int *__restrict__ bcolind, const double *__restrict__ vals,
+                      const double *__restrict__ x, const double a, const double b, const double *yin,
+                      double *z)
+{
+	constexpr int BS = 4, GPW = 8, BS2 = 16, PK = 6;
+	const int lane = threadIdx.x & 31;
+	const int g = lane >> 2, r = lane & 3;
+	const int wpc = blockDim.x >> 5;
+	const long long stride = (long long)gridDim.x*wpc*GPW;
+	const long long wbase = ((long long)blockIdx.x*wpc + (threadIdx.x >> 5))*GPW;
+
+	auto load_meta = [&](const long long t, int& js, int& je) {
+		js = 0; je = 0;
+		if(t < nbrows) { js = __ldg(browptr + t); je = __ldg(browptr + t + 1); }
+	};
+	auto load_cols = [&](const int js, const int je, int (&c)[PK]) {
+#pragma unroll
+		for(int q = 0; q < PK; q++) c[q] = (js + q < je) ? __ldg(bcolind + js + q) : 0;
+	};
+	int js1, je1, c1[PK], js2, je2;
+	load_meta(wbase + g, js1, je1);
+	load_cols(js1, je1, c1);
+	load_meta(wbase + g + stride, js2, je2);
+
+	for(long long tw = wbase; tw < nbrows; tw += stride) {
+		const long long t = tw + g;
+		const int js = js1, je = je1;
+		int cols[PK];
+#pragma unroll
+		for(int q = 0; q < PK; q++) cols[q] = c1[q];
+		js1 = js2; je1 = je2;
+		load_cols(js1, je1, c1);
+		load_meta(t + 2*stride, js2, je2);
+		if(t >= nbrows) continue;
+		double acc = 0;
+#pragma unroll
+		for(int q = 0; q < PK; q++) {
+			const int jj = js + q;
+			if(jj < je) {
+				double av[BS], xv[BS];
+				BlkIO<BS>::template load_row<false>(vals + (size_t)jj*BS2, r, av);
+				load_seg<BS,false,true>(x + (size_t)cols[q]*BS, xv);
+#pragma unroll
+				for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+			}
+		}
+		for(int jj = js + PK; jj < je; jj++) {
+			const int col = __ldg(bcolind + jj);
+			double av[BS], xv[BS];
+			BlkIO<BS>::template load_row<false>(vals + (size_t)jj*BS2, r, av);
+			load_seg<BS,false,true>(x + (size_t)col*BS, xv);
+#pragma unroll
+			for(int c = 0; c < BS; c++) acc = fma(av[c], xv[c], acc);
+		}
+		const size_t o = (size_t)t*BS + r;
+		if(G3) z[o] = a*acc + b*yin[o];
+		else z[o] = acc;
+	}
+}
+
 template <bool G3>
 static void launch_csr(const Mat& A, double a, const double *x, double b, const double *y, double *z,
                        cudaStream_t st)
@@ -107,7 +175,21 @@ static void launch_bsr(const Mat& A, double a, const double *x, double b, const 
 	constexpr int GPW = 32/BS;
 	const long long nwarps = ((long long)A.nbrows + GPW - 1)/GPW;
 	const int grid = div_up(nwarps*32, 256);
-	if(BS == 4 && aligned32(x))
+	static const bool one_shot = getenv("B200_SPMV1") != nullptr;        // A/B switch (development)
+	if(BS == 4 && aligned32(x) && !one_shot && A.nbrows >= 4096) {
+		static int resident = 0;
+		if(!resident) {
+			int dev = 0, sms = 148, per = 4;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, bsr4_spmv_pipe_kernel<G3>, 256, 0) != cudaSuccess || per < 1)
+				per = 4;
+			resident = sms*per;
+		}
+		const int pg = (int)std::min<long long>(resident, (A.nbrows + 63)/64);
+		bsr4_spmv_pipe_kernel<G3><<<pg, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
+	}
+	else if(BS == 4 && aligned32(x))
 		bsr_spmv_kernel<BS,G3,true><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
 	else
 		bsr_spmv_kernel<BS,G3,false><<<grid, 256, 0, st>>>(A.nbrows, A.browptr, A.bcolind, A.vals, x, a, b, y, z);
