@@ -115,4 +115,87 @@ void B200MatrixView::gemv3(const double a, const double *const __restrict x, con
 	check_runtime(b200_mat_gemv3_host(dmat, a, x, b, y, z));
 }
 
+
+// ---- reordering / scaling on the device behind the reference's ReorderingScaling interface
+
+namespace {
+
+void check_b200(const int rc)
+{
+	if(rc) throw std::runtime_error(b200_last_error());
+}
+
+/// host matrix -> device, transform, -> the same host arrays
+template <typename F>
+void on_device_matrix(blasted::RawBSRMatrix<double,int>& mat, const int bs, F&& transform)
+{
+	b200_mat *dm = nullptr;
+	// blocks are moved / scaled as opaque bs*bs chunks: the layout flag does not matter here
+	check_b200(b200_mat_create_host(mat.nbrows, bs, B200_COLMAJOR, mat.browptr, mat.bcolind, mat.vals,
+	                                nullptr, &dm));
+	try {
+		transform(dm);
+		check_b200(b200_mat_get_host(dm, mat.browptr, mat.bcolind, mat.diagind, mat.vals));
+	} catch(...) { b200_mat_destroy(dm); throw; }
+	b200_mat_destroy(dm);
+}
+
+}
+
+template <int bs>
+void B200ReorderingScaling<bs>::setScaling(const double *const rscale, const double *const cscale,
+                                           const int length)
+{
+	if(rscale) rowscale.assign(rscale, rscale + length);
+	if(cscale) colscale.assign(cscale, cscale + length);
+}
+
+template <int bs>
+void B200ReorderingScaling<bs>::applyOrdering(blasted::RawBSRMatrix<double,int>& mat,
+                                              const blasted::RSApplyMode mode) const
+{
+	if(rp.empty() && cp.empty()) return;
+	on_device_matrix(mat, bs, [&](b200_mat *dm) {
+		check_b200(b200_mat_reorder(dm, rp.empty() ? nullptr : rp.data(), cp.empty() ? nullptr : cp.data(),
+		                            mode == blasted::INVERSE ? 1 : 0, 0));
+	});
+}
+
+template <int bs>
+void B200ReorderingScaling<bs>::applyOrdering(double *const vec, const blasted::RSApplyMode mode,
+                                              const blasted::RSApplyDir dir) const
+{
+	const std::vector<int>& ord = (dir == blasted::ROW) ? rp : cp;
+	if(ord.empty()) return;
+	check_b200(b200_vec_reorder(vec, (long long)ord.size(), bs, ord.data(),
+	                            mode == blasted::INVERSE ? 1 : 0, 0));
+}
+
+template <int bs>
+void B200ReorderingScaling<bs>::applyScaling(blasted::RawBSRMatrix<double,int>& mat,
+                                             const blasted::RSApplyMode mode) const
+{
+	if(rowscale.empty() && colscale.empty()) return;
+	on_device_matrix(mat, bs, [&](b200_mat *dm) {
+		check_b200(b200_mat_scale(dm, rowscale.empty() ? nullptr : rowscale.data(),
+		                          colscale.empty() ? nullptr : colscale.data(),
+		                          mode == blasted::INVERSE ? 1 : 0, 0));
+	});
+}
+
+template <int bs>
+void B200ReorderingScaling<bs>::applyScaling(double *const vec, const blasted::RSApplyMode mode,
+                                             const blasted::RSApplyDir dir) const
+{
+	const std::vector<double>& sc = (dir == blasted::ROW) ? rowscale : colscale;
+	if(sc.empty()) return;
+	check_b200(b200_vec_scale(vec, (long long)sc.size(), bs, sc.data(),
+	                          mode == blasted::INVERSE ? 1 : 0, 0));
+}
+
+// the block sizes the reference instantiates (src/reorderingscaling.cpp:268-270, 370-372)
+template class B200ReorderingScaling<1>;
+template class B200ReorderingScaling<4>;
+template class B200ReorderingScaling<7>;
+
 }

@@ -7,6 +7,7 @@
  *   B200Preconditioner : blasted::SRPreconditioner<double,int>   include/solverops_base.hpp:68-78
  *   B200Factory        : blasted::FactoryBase<double,int>        include/solverfactory.hpp:71-85
  *   B200MatrixView     : blasted::SRMatrixView<double,int>       include/blockmatrices.hpp:27-60
+ *   B200ReorderingScaling<bs> : blasted::ReorderingScaling<double,int,bs>  include/reorderingscaling.hpp:106-133
  * so the PETSc PCSHELL glue (src/blasted_petsc.cpp:216-327, 474-576), tests/testsolve.cpp:86-88 and the
  * Krylov drivers of tests/solvers.cpp use them unchanged.  Pointers handed to apply()/apply_relax()
  * are HOST pointers, as in the reference; copies to and from the device happen inside the call.
@@ -20,6 +21,7 @@
 #include "solverfactory.hpp"
 #include "solverops_base.hpp"
 #include "blockmatrices.hpp"
+#include "reorderingscaling.hpp"
 #include "../../include/blasted_b200.h"
 
 namespace blasted_b200 {
@@ -84,6 +86,30 @@ protected:
 	using blasted::SRMatrixView<double,int>::mat;
 	int bs;
 	b200_mat *dmat;
+};
+
+/// Reordering / scaling of host matrices and vectors carried out on the device: same virtuals,
+/// same conventions as the reference classes (include/reorderingscaling.hpp:36-133,
+/// src/reorderingscaling.cpp:77-368).  As in the reference the orderings and scalings themselves come
+/// from outside (setOrdering, setScaling); compute() is a no-op.  One difference: the matrix'
+/// diagind array, which the reference leaves stale after a permutation, is located again.
+template <int bs>
+class B200ReorderingScaling : public blasted::ReorderingScaling<double,int,bs>
+{
+public:
+	void compute(const blasted::CRawBSRMatrix<double,int>&) override { }
+	void setScaling(const double *const rscale, const double *const cscale, const int length);
+	void applyOrdering(blasted::RawBSRMatrix<double,int>& mat, const blasted::RSApplyMode mode) const override;
+	void applyOrdering(double *const vec, const blasted::RSApplyMode mode,
+	                   const blasted::RSApplyDir dir) const override;
+	void applyScaling(blasted::RawBSRMatrix<double,int>& mat, const blasted::RSApplyMode mode) const override;
+	void applyScaling(double *const vec, const blasted::RSApplyMode mode,
+	                  const blasted::RSApplyDir dir) const override;
+protected:
+	using blasted::ReorderingScaling<double,int,bs>::rp;
+	using blasted::ReorderingScaling<double,int,bs>::cp;
+	using blasted::ReorderingScaling<double,int,bs>::rowscale;
+	using blasted::ReorderingScaling<double,int,bs>::colscale;
 };
 
 }

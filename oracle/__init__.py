@@ -407,6 +407,7 @@ class _Ref:
         L.ref_srmat_copy.argtypes = [vp, _ip, _ip, _ip, _dp]
         L.ref_srmat_destroy.argtypes = [vp]
         L.ref_reorder_scale.argtypes = [C.c_int, C.c_int] + [vp] * 8 + [C.c_int, vp, vp]
+        L.ref_reorder_scale_b200.argtypes = L.ref_reorder_scale.argtypes
 
     # ---- front end ----
     def read_mtx(self, path, bs, rowmajor=False):
@@ -424,8 +425,9 @@ class _Ref:
         return browptr, bcolind[:nnzb], diagind[:nb], vals[:nnzb * bs * bs]
 
     def reorder_scale(self, m, rord=None, cord=None, rowscale=None, colscale=None, inverse=False,
-                      rowvec=None, colvec=None):
-        """Reordering / ReorderingScaling applied to copies -> (browptr, bcolind, vals, rowvec, colvec)"""
+                      rowvec=None, colvec=None, through_b200=False):
+        """Reordering / ReorderingScaling applied to copies -> (browptr, bcolind, vals, rowvec, colvec);
+        through_b200: the product's device adapter behind the same reference interface."""
         def ia(a):
             return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
 
@@ -433,7 +435,8 @@ class _Ref:
             return None if a is None else np.array(a, dtype=np.float64)
         bp, bc, v, di = m.browptr.copy(), m.bcolind.copy(), m.vals.copy(), m.diagind.copy()
         ro, co, rs, cs, rv, cv = ia(rord), ia(cord), da(rowscale), da(colscale), da(rowvec), da(colvec)
-        rc = self.lib.ref_reorder_scale(m.bs, m.nbrows, _opt(bp), _opt(bc), _opt(v), _opt(di), _opt(ro),
+        fn = self.lib.ref_reorder_scale_b200 if through_b200 else self.lib.ref_reorder_scale
+        rc = fn(m.bs, m.nbrows, _opt(bp), _opt(bc), _opt(v), _opt(di), _opt(ro),
                                         _opt(co), _opt(rs), _opt(cs), int(inverse), _opt(rv), _opt(cv))
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())

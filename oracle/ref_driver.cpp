@@ -92,12 +92,12 @@ struct SetOrderingScaling : public ReorderingScaling<double,int,bs> {
 	}
 };
 
-template <int bs>
+template <int bs, typename RS = SetOrderingScaling<bs>>
 void ref_reorder_scale(int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
                        const int *rord, const int *cord, const double *rs, const double *cs,
                        int inverse, double *rowvec, double *colvec)
 {
-	SetOrderingScaling<bs> r;
+	RS r;
 	r.setOrdering(rord, cord, nbrows);
 	r.setScaling(rs, cs, nbrows);
 	const RSApplyMode mode = inverse ? INVERSE : FORWARD;
@@ -437,6 +437,22 @@ void ref_srmat_copy(void *hh, int *browptr, int *bcolind, int *diagind, double *
 	for(long long i = 0; i < (long long)nz*bs2; i++) vals[i] = h->m.vals[i];
 }
 void ref_srmat_destroy(void *hh) { delete static_cast<RefSRMat*>(hh); }
+
+/// The same through the product's device implementation behind the reference's own interface
+/// (blasted_b200/host: B200ReorderingScaling<bs> : ReorderingScaling<double,int,bs>)
+int ref_reorder_scale_b200(int bs, int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
+                           const int *rord, const int *cord, const double *rowscale,
+                           const double *colscale, int inverse, double *rowvec, double *colvec)
+{
+	using namespace blasted_b200;
+	try {
+		if(bs == 1) ref_reorder_scale<1,B200ReorderingScaling<1>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else if(bs == 4) ref_reorder_scale<4,B200ReorderingScaling<4>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else if(bs == 7) ref_reorder_scale<7,B200ReorderingScaling<7>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
+		else { g_err = "Reordering: only bs 1,4,7 instantiated in the reference"; return 1; }
+	} catch(std::exception& e) { g_err = e.what(); return 1; }
+	return 0;
+}
 
 /// Reordering / ReorderingScaling (src/reorderingscaling.cpp) applied in place to a matrix (may be
 /// null) and to a row-direction and a column-direction vector (may be null).  Scaling is applied

@@ -247,3 +247,26 @@ def test_full_size_c2_conversion_and_round_trip():
     assert np.array_equal(hm.diagind >= 0, np.ones(nb, dtype=bool))
     ro.applyOrdering(view, INVERSE)
     same_matrix(view, m.browptr, m.bcolind, m.diagind, m.vals)
+
+
+@pytest.mark.parametrize("case", [("2dcyl1", 1), ("2dcyl1", 4), ("DK01R", 7)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_reordering_scaling_adapter_behind_reference_interface(case, inverse):
+    """B200ReorderingScaling<bs> (blasted_b200/host) derives from the reference's
+    ReorderingScaling<double,int,bs>; driven through the reference's own virtuals it must give the
+    reference's results bit for bit (matrix arrays, row- and column-direction vectors)."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("reference build not present")
+    name, bs = case
+    m = load(name, bs)
+    rng = np.random.default_rng(21)
+    rord = rng.permutation(m.nbrows).astype(np.int32)
+    cord = rng.permutation(m.nbrows).astype(np.int32)
+    rs, cs = rng.uniform(0.5, 2.0, m.nbrows), rng.uniform(0.5, 2.0, m.nbrows)
+    vec = rng.standard_normal(m.dim)
+    kw = dict(rord=rord, cord=cord, rowscale=rs, colscale=cs, inverse=inverse, rowvec=vec, colvec=vec)
+    want = oracle.ref().reorder_scale(m, **kw)
+    got = oracle.ref().reorder_scale(m, through_b200=True, **kw)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
