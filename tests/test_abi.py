@@ -24,6 +24,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(_lib.lib, n), f"{n} declared in include/blasted_b200.h but not exported"
     # and the Python binding table covers the header exactly
     assert sorted(_lib.SYMBOLS) == names
+    # the PETSc-free PCSHELL core (include/blasted_b200_shell.h) lives in the same library
+    txt = open(os.path.join(ROOT, "include", "blasted_b200_shell.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    shell = sorted(set(re.findall(r"\b(b200_shell_[a-z0-9_]+)\s*\(", txt)))
+    assert len(shell) >= 15
+    for n in shell:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/blasted_b200_shell.h but not exported"
 
 
 def test_no_oracle_in_product_path():
