@@ -425,7 +425,8 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 	while(true) {
 		// While a warp waits, only its first unfinished lane polls (its next dependency): the rows
 		// of a warp are level-sorted, so that lane becomes ready first, and tens of thousands of
-		// waiting rows polling all their dependencies saturate L2 and stretch every hand-over.
+		// waiting rows polling all their dependencies saturate L2 and stretch every hand-over
+		// (a sleep between polls was measured too: 0 / 32 / 100 / 300 ns make no difference or lose).
 		const unsigned waiting = __ballot_sync(0xffffffffu, !stored && cbase < je);
 		if(waiting) {
 			const int leader = __ffs(waiting) - 1;
@@ -439,7 +440,6 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 			ready = __shfl_sync(0xffffffffu, ready, leader);
 			const bool somebody_done = __any_sync(0xffffffffu, !stored && cbase >= je);
 			if(!ready && !somebody_done) {
-				__nanosleep(32);
 				if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
 					if(spins > (1 << 22) || *((volatile int*)err)) { *err = 1; cbase = je; }
 				}
