@@ -106,3 +106,38 @@ def test_reorder_round_trip_and_spmv_property():
     # inverse undoes forward, bit for bit
     bp2, bc2, v2 = o.reorder_matrix(pm, rord, cord, True)
     assert np.array_equal(bp2, m.browptr) and np.array_equal(bc2, m.bcolind) and np.array_equal(v2, m.vals)
+
+
+def test_matrix_market_reader_host_side(tmp_path):
+    """The text parsing is host work (blasted_b200.frontend.COOMatrix.readMatrixMarket): it accepts
+    what the reference's reader accepts and refuses what it refuses (src/coomatrix.cpp:189-221)."""
+    from blasted_b200.frontend import COOMatrix, MatrixReadException
+    m = load_fixture("small_block3", 1)
+    r, c, v = triplets(m, 4)
+    path = os.path.join(tmp_path, "a.mtx")
+    write_mtx(path, m.dim, r, c, v)
+    coo = COOMatrix()
+    coo.readMatrixMarket(path)
+    assert (coo.numrows(), coo.numcols(), coo.numnonzeros()) == (m.dim, m.dim, len(v))
+    assert np.array_equal(coo.rowind, r) and np.array_equal(coo.colind, c) and np.array_equal(coo.values, v)
+    if oracle.have_ref():
+        # the parsed triplets, converted by the oracle, are what the reference reads from the file
+        ref = oracle.ref().read_mtx(path, 3, False)
+        got = oracle.orc().coo_convert(coo.numrows(), coo.rowind, coo.colind, coo.values, 3, False)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
+    for banner, msg in [("%%MatrixMarket matrix array real general", "coordinate storage"),
+                        ("%%MatrixMarket matrix coordinate pattern general", "pattern"),
+                        ("%%MatrixMarket matrix coordinate real symmetric", "general matrices"),
+                        ("%%MatrixMarket matrix coordinate complex general", "complex"),
+                        ("%%NotMatrixMarket matrix coordinate real general", "not a Matrix Market")]:
+        bad = os.path.join(tmp_path, "bad.mtx")
+        with open(bad, "w") as f:
+            f.write(banner + "\n2 2 1\n1 1 1.0\n")
+        with pytest.raises(MatrixReadException, match=msg):
+            COOMatrix().readMatrixMarket(bad)
+    short = os.path.join(tmp_path, "short.mtx")
+    with open(short, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n3 3 4\n1 1 1.0\n2 2 1.0\n")
+    with pytest.raises(MatrixReadException, match="fewer entries"):
+        COOMatrix().readMatrixMarket(short)
