@@ -144,7 +144,12 @@ void prec_compute(Prec& P, double precinfo[6])
 		else if(P.s.nbuildsweeps > 0 && scalar && exact_in_one_launch(P)) {
 			// exact factorisation: one launch over the level-sorted rows (scalar_ilu.cu)
 			if(!P.rowdone.p) P.rowdone.alloc(std::max(A.nbrows, 1));
+			B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), st));
 			scalar_ilu0_exact(A, P.pl, P.levels.level_rows, scale, P.sf, P.rowdone, P.sync_flags, st);
+			int failed = 0;      // the sweeps path synchronises too (every fourth sweep)
+			B200_CUDA(cudaMemcpyAsync(&failed, P.sync_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+			B200_CUDA(cudaStreamSynchronize(st));
+			if(failed) throw Error("exact factorisation did not complete: a dependency never arrived");
 			P.factor_sweeps_done = 1;
 		}
 		else if(P.s.nbuildsweeps > 0) {
@@ -280,6 +285,9 @@ static void exact_pair(Prec& P, TriKind lower, TriKind upper, TriArgs aL, TriArg
 	aL.row_begin = aU.row_begin = 0; aL.row_end = aU.row_end = n;
 	aL.rhs = r; aL.x = P.ytemp; aL.descending = false;
 	aU.rhs = P.ytemp; aU.x = z; aU.descending = true;
+	// a failure of an earlier call was reported then (b200_prec_apply_host) or is the caller's to
+	// fetch; start clean so that one bad call does not poison the object
+	B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), P.stream));
 	double *zz = z;
 	if(z == r) {                       // in-place call: the upper solve may not overwrite r early
 		if(!P.lev_z.p) { P.lev_r.alloc(P.A->dim()); P.lev_z.alloc(P.A->dim()); }
