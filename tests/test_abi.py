@@ -65,3 +65,32 @@ def test_factory_strings():
     assert f.solverTypeFromString("ilu0") == 3 and f.solverTypeFromString("none") == 10
     with pytest.raises(ValueError):
         f.solverTypeFromString("bogus")
+
+
+def _build_c_example(tmp_path):
+    """The headers are plain C99 and the library links from C (what cgo / JNI / ctypes stubs need)."""
+    import subprocess
+    exe = os.path.join(tmp_path, "c_abi_example")
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_example.c"),
+           "-L" + os.path.join(ROOT, "blasted_b200"), "-lblasted_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "blasted_b200"), "-lm", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_c_example_compiles_and_links(tmp_path):
+    import subprocess
+    import blasted_b200 as bb
+    exe = _build_c_example(tmp_path)
+    rc = subprocess.run([exe], capture_output=True, text=True).returncode
+    assert rc == (0 if bb.device_count() > 0 else 77)
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "|z_abi - z_shell| = 0.000e+00" in out.stdout
