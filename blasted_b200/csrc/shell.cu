@@ -234,7 +234,9 @@ int b200_shell_setup(b200_shell_node *node, int bs, int nbrows, const int *ia, c
 		if(!node) throw std::runtime_error("null argument");
 		if(!node->first_setup_done)
 			throw std::runtime_error("shell: b200_shell_set_options must come before the first setup");
+		bool created = false;
 		if(!node->bprec) {
+			created = true;
 			// createNewPreconditioner, :216-311
 			if(bs <= 0 || bs > 5 || bs == 2)
 				throw std::runtime_error("BLASTed: Block size " + std::to_string(bs) + " is not supported!");
@@ -259,7 +261,7 @@ int b200_shell_setup(b200_shell_node *node, int bs, int nbrows, const int *ia, c
 			throw std::runtime_error("shell: the local matrix changed size between setups");
 		Stopwatch sw;
 		// updatePreconditioner, :314-327: PETSc has rewritten `a` in place; same pattern
-		if(node->bprec && a) need(b200_mat_update_values_host(node->bmat, a));
+		if(!created && a) need(b200_mat_update_values_host(node->bmat, a));   // (creation uploaded them)
 		double info[6] = {0, 0, 0, 0, 0, 0};
 		need(b200_prec_compute(node->bprec, info));
 		if(node->infolist) {
