@@ -33,9 +33,37 @@ NBUILD, NAPPLY = 3, 3
 
 # ----------------------------------------------------------------------------- workload + bytes
 
+def load_matgen():
+    """blasted_b200/matgen.py is pure numpy; it is loaded by path so that the reference arm does not
+    import the package (which would map libblasted_b200.so into that process)."""
+    import importlib.util
+    if "b200_matgen" in sys.modules:
+        return sys.modules["b200_matgen"]
+    spec = importlib.util.spec_from_file_location(
+        "b200_matgen", os.path.join(ROOT, "blasted_b200", "matgen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["b200_matgen"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_matrix(rank, cells):
-    from blasted_b200 import matgen
-    return matgen.block_stencil((cells, cells), 4, SEED + 1000*rank)
+    return load_matgen().block_stencil((cells, cells), 4, SEED + 1000*rank)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+REF_KIND = "reference"     # the driver's vocabulary; what it is exactly goes into `build`
+REF_BUILD = ("unmodified reference sources (OpenMP) compiled against the Eigen/Boost header shim of "
+             "oracle/shim, g++ -O3 -march=x86-64-v3")
 
 
 def reference_bytes(m, npos, nbuild, napply):
@@ -160,7 +188,7 @@ def cpu_step_time(m, steps, warmup, nbuild, napply):
             if it >= warmup:
                 ts.append(time.perf_counter() - t0)
         p.close()
-        return float(np.mean(ts)), "reference", cores
+        return float(np.mean(ts)), REF_KIND, cores
     O = orc()
     plist = O.ilu_positions(m)
     ts = []
@@ -183,14 +211,16 @@ def run_reference(args):
     m = make_matrix(0, cells)
     npos = 2*(cells*cells) - 2*cells                      # 5-point stencil: 2 products per diagonal
     by = reference_bytes(m, npos, NBUILD, NAPPLY)
-    sec, kind, cores = cpu_step_time(m, args.steps, min(args.warmup, 1), NBUILD, NAPPLY)
+    sec, kind, cores = cpu_step_time(m, args.steps, args.warmup, NBUILD, NAPPLY)
     val = by["step"]/sec/1e9
     line = {"impl": "reference", "metric": "async_ilu0_factor_apply_hbm_gbs", "value": val,
-            "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec*1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(m, cells),
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind,
+                             "build": REF_BUILD if kind == REF_KIND else "oracle port (plain C, 1 thread)",
+                             "cpu_model": cpu_model(),
                              "sample": f"full C2 step ({NBUILD} factor sweeps + {NAPPLY} apply sweep "
                                        f"pairs) x {args.steps} on the host cores"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -356,7 +386,8 @@ def run_b200(args):
         csteps = 2
         sec, kind, cores = cpu_step_time(m, csteps, 1, NBUILD, NAPPLY)
         cpu = {"value": ref_by["step"]/sec/1e9, "unit": "GB/s", "cores": cores, "kind": kind,
-               "ms_per_step": sec*1e3,
+               "build": REF_BUILD if kind == REF_KIND else "oracle port (plain C, 1 thread)",
+               "cpu_model": cpu_model(), "ms_per_step": sec*1e3,
                "sample": f"full C2 step x {csteps} (1 warm-up) on the host cores, same matrix"}
 
     line = {"metric": "async_ilu0_factor_apply_hbm_gbs", "value": value, "unit": "GB/s",

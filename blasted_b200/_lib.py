@@ -66,6 +66,7 @@ SYMBOLS = {
     "b200_prec_set_apply_params": (_i, [_vp, _d, _d, _d, _i, _i]),
     "b200_prec_apply_relax": (_i, [_vp, _vp, _vp, _i]),
     "b200_prec_apply_relax_host": (_i, [_vp, _vp, _vp, _i]),
+    "b200_prec_check": (_i, [_vp]),
     "b200_prec_dim": (_i, [_vp]),
     "b200_prec_relaxation_available": (_i, [_vp]),
     "b200_prec_destroy": (None, [_vp]),

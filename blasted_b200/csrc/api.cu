@@ -138,6 +138,9 @@ struct LocalOps : public KrylovOps {
 	LocalOps(const Mat *A_, Prec *M_) : A(A_), M(M_) {
 		n = A->dim();
 		stream = A->stream;
+		if(M && M->stream != A->stream)
+			throw Error("solve: the matrix and the preconditioner are on different streams "
+			            "(set both with b200_mat_set_stream / b200_prec_set_stream)");
 		ws = &A->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
 		dout.alloc(MAX_KRYLOV_DOTS);
@@ -151,13 +154,19 @@ struct LocalOps : public KrylovOps {
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
 	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
+		const double *d = dots_device(nd, a, b);
+		B200_CUDA(cudaMemcpyAsync(out, d, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
+		B200_CUDA(cudaStreamSynchronize(stream));
+		return d;
+	}
+	const double *dots_device(int nd, const double *const *a, const double *const *b) override {
 		if(nd > MAX_KRYLOV_DOTS) throw Error("dots: too many products");
 		for(int o = 0; o < nd; o += MAX_DOTS)
 			launch_multi_dot(n, std::min(MAX_DOTS, nd - o), a + o, b + o, partial, dout.p + o, stream);
-		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
-		B200_CUDA(cudaStreamSynchronize(stream));
 		return dout.p;
 	}
+	bool prec_reads_output() const override { return M && prec_sweeps_in_place(*M); }
+	void check_prec() override { if(M) prec_check(*M); }
 };
 
 namespace {
@@ -491,11 +500,8 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z)
 			B200_CUDA(cudaMemcpyAsync(P.hz, z, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
 		prec_apply(P, P.hr, P.hz);
 		B200_CUDA(cudaMemcpyAsync(z, P.hz, n*sizeof(double), cudaMemcpyDeviceToHost, P.stream));
-		int flag = 0;
-		if(P.sync_flags.p)
-			B200_CUDA(cudaMemcpyAsync(&flag, P.sync_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, P.stream));
 		B200_CUDA(cudaStreamSynchronize(P.stream));
-		if(flag) throw Error("exact substitution did not complete: a dependency never arrived");
+		prec_check(P);
 	});
 }
 
@@ -525,6 +531,8 @@ int b200_prec_set_apply_params(b200_prec *p, double rtol, double atol, double dt
 	return 0;
 }
 
+int b200_prec_check(b200_prec *p) { return guarded([&] { prec_check(p->p); }); }
+
 int b200_prec_dim(const b200_prec *p) { return p->p.dim(); }
 
 int b200_prec_relaxation_available(const b200_prec *p)
@@ -539,6 +547,8 @@ void b200_prec_destroy(b200_prec *p)
 	if(!p) return;
 	if(p->p.ev0) cudaEventDestroy(p->p.ev0);
 	if(p->p.ev1) cudaEventDestroy(p->p.ev1);
+	if(p->p.evc0) cudaEventDestroy(p->p.evc0);
+	if(p->p.evc1) cudaEventDestroy(p->p.evc1);
 	for(void *g : p->p.level_graph) if(g) cudaGraphExecDestroy((cudaGraphExec_t)g);
 	if(p->p.cap_stream) cudaStreamDestroy(p->p.cap_stream);
 	delete p;
@@ -659,7 +669,14 @@ int b200_prec_last_times(b200_prec *p, double *compute_ms, double *apply_ms)
 {
 	return guarded([&] {
 		Prec& P = p->p;
-		if(compute_ms) *compute_ms = P.compute_ms;
+		if(compute_ms) {
+			if(P.compute_timed && P.evc1 && cudaEventSynchronize(P.evc1) == cudaSuccess) {
+				float ms = 0;
+				if(cudaEventElapsedTime(&ms, P.evc0, P.evc1) == cudaSuccess) P.compute_ms = ms;
+			}
+			cudaGetLastError();
+			*compute_ms = P.compute_ms;
+		}
 		if(apply_ms) {
 			*apply_ms = 0;
 			if(P.ev1 && cudaEventSynchronize(P.ev1) == cudaSuccess) {

@@ -174,6 +174,40 @@ multi_axpy_kernel(const long long n, const int nv, const AxpyPtrs p, const doubl
 	y[i] = s;
 }
 
+/// out = (y + sign * sum_l coef[l] v_l) * (*scale): the Gram-Schmidt update and the normalisation of
+/// the new basis vector in one pass (y itself is not rewritten)
+__global__ void __launch_bounds__(256)
+multi_axpy_scaled_kernel(const long long n, const int nv, const AxpyPtrs p,
+                         const double *__restrict__ coef, const double *__restrict__ y,
+                         double *__restrict__ out, const double sign, const double *__restrict__ scale)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double s = y[i];
+	for(int l = 0; l < nv; l++) s = fma(sign*__ldg(coef + l), p.v[l][i], s);
+	out[i] = s*__ldg(scale);
+}
+
+/// After the fused Gram-Schmidt multi-dot of FGMRES iteration j: dots[0..j] = v_i.w, dots[j+1] = w.w.
+/// Writes column j of the Hessenberg matrix {h_0..h_j, |w - sum h_i v_i|, cancellation flag} and
+/// the reciprocal norm for the normalisation - on the device, so that the host need not wait.
+__global__ void fgmres_column_kernel(const int j, const double *__restrict__ dots,
+                                     double *__restrict__ hcol, const int hn_slot,
+                                     double *__restrict__ inv_hn)
+{
+	if(threadIdx.x != 0 || blockIdx.x != 0) return;
+	double sumsq = 0;
+	for(int i = 0; i <= j; i++) { const double h = dots[i]; hcol[i] = h; sumsq = fma(h, h, sumsq); }
+	const double ww = dots[j+1], hn2 = ww - sumsq;
+	// |w_new|^2 = w.w - sum h_i^2 (V orthonormal); more than four digits lost to cancellation (or
+	// a non-finite value) is flagged for the host, which redoes the iteration with an explicit norm
+	const bool ok = hn2 > 1e-4*ww;
+	const double hn = ok ? sqrt(hn2) : 0.0;
+	hcol[hn_slot] = hn;
+	hcol[hn_slot + 1] = ok ? 0.0 : 1.0;
+	*inv_hn = hn > 0 ? 1.0/hn : 0.0;
+}
+
 __global__ void vec_scal_kernel(const long long n, const double alpha, const double *__restrict__ in,
                                 double *__restrict__ out)
 {
@@ -218,6 +252,25 @@ void launch_vec_scal(long long n, double alpha, const double *in, double *out, c
 {
 	if(n == 0) return;
 	vec_scal_kernel<<<div_up(n,256),256,0,st>>>(n, alpha, in, out);
+	B200_LAUNCHED();
+}
+
+void launch_multi_axpy_scaled(long long n, int nv, const double *const *v, const double *d_coef,
+                              const double *y, double *out, const double *d_scale, cudaStream_t st,
+                              double sign)
+{
+	if(n == 0) return;
+	if(nv > 32) throw Error("multi_axpy: too many vectors");
+	AxpyPtrs p;
+	for(int l = 0; l < 32; l++) p.v[l] = v[l < nv ? l : 0];
+	multi_axpy_scaled_kernel<<<div_up(n,256),256,0,st>>>(n, nv, p, d_coef, y, out, sign, d_scale);
+	B200_LAUNCHED();
+}
+
+void launch_fgmres_column(int j, const double *d_dots, double *d_hcol, int hn_slot, double *d_inv_hn,
+                          cudaStream_t st)
+{
+	fgmres_column_kernel<<<1,32,0,st>>>(j, d_dots, d_hcol, hn_slot, d_inv_hn);
 	B200_LAUNCHED();
 }
 

@@ -108,13 +108,17 @@ struct KrylovStore {
 	long long stride = 0;                                   ///< doubles per vector (even: 16-byte aligned)
 	std::vector<std::unique_ptr<DevBuf<double>>> chunks;
 	void release() { chunks.clear(); stride = 0; }
-	double *vec(long long n, int i) {
+	/// New chunks are zero-filled on `st` (the reference's work vectors are value-initialised
+	/// std::vectors, tests/solvers.cpp:264-270, and some preconditioners sweep in place on them)
+	double *vec(long long n, int i, cudaStream_t st) {
 		const long long need = (n + 1) & ~1LL;
 		if(need != stride) { release(); stride = need; }
 		const size_t c = (size_t)i / PER_CHUNK;
 		while(chunks.size() <= c) {
 			chunks.emplace_back(new DevBuf<double>());
-			chunks.back()->alloc((size_t)std::max<long long>(stride, 2)*PER_CHUNK);
+			const size_t cnt = (size_t)std::max<long long>(stride, 2)*PER_CHUNK;
+			chunks.back()->alloc(cnt);
+			B200_CUDA(cudaMemsetAsync(chunks.back()->p, 0, cnt*sizeof(double), st));
 		}
 		return chunks[c]->p + (size_t)(i % PER_CHUNK)*stride;
 	}
@@ -310,6 +314,13 @@ void launch_multi_dot(long long n, int nd, const double *const *a, const double 
 /// y += sum_l coef[l] * v[l]  for l < nv (coefficients read from device memory), nv <= 32 per call
 void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef,
                        double *y, cudaStream_t st, double sign = 1.0);
+/// out = (y + sign * sum_l coef[l] v[l]) * (*d_scale), nv <= 32; y is not modified
+void launch_multi_axpy_scaled(long long n, int nv, const double *const *v, const double *d_coef,
+                              const double *y, double *out, const double *d_scale, cudaStream_t st,
+                              double sign = 1.0);
+/// FGMRES iteration j, device side: Hessenberg column + reciprocal norm from the fused multi-dot
+void launch_fgmres_column(int j, const double *d_dots, double *d_hcol, int hn_slot, double *d_inv_hn,
+                          cudaStream_t st);
 /// x = xtemp, returning sum (xtemp - x)^2 in d_out[0] (Jacobi relaxation with tolerance checks)
 void launch_update_diffnorm(long long n, const double *xtemp, double *x, double *d_out, cudaStream_t st);
 /// out = alpha * in
@@ -337,7 +348,9 @@ struct Prec {
 	double rtol = 0, atol = 0, dtol = 1e30;
 	bool ctol = false;
 	int maxits = 1;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;      ///< around the last apply()
+	cudaEvent_t evc0 = nullptr, evc1 = nullptr;    ///< around the last compute() (read lazily)
+	bool compute_timed = false;
 	double compute_ms = 0, apply_ms = 0;
 	// level-scheduled applies replayed as CUDA graphs (precond.cu::run_level_graph)
 	DevBuf<double> lev_r, lev_z;
@@ -349,6 +362,12 @@ struct Prec {
 	int dim() const { return A->nbrows*A->bs; }
 };
 
+/// apply() sweeps in place on what z holds on entry (ChaoticRelaxation::apply; SGS with INIT_A_NONE)
+inline bool prec_sweeps_in_place(const Prec& P)
+{
+	return P.s.prectype == B200_GS || (P.s.prectype == B200_SGS && P.s.apply_inittype == B200_INIT_A_NONE);
+}
+
 }  // namespace b200
 // the opaque handles of the C ABI
 struct b200_mat { b200::Mat m; };
@@ -358,6 +377,9 @@ namespace b200 {
 void prec_compute(Prec& P, double precinfo[6]);
 void prec_apply(Prec& P, const double *d_r, double *d_z);
 void prec_apply_relax(Prec& P, const double *d_b, double *d_x, int maxits);
+/// Synchronises the handle's stream and raises (once) if a one-launch exact substitution recorded a
+/// dependency that never arrived since the last check
+void prec_check(Prec& P);
 
 // ---------------------------------------------------------------- Krylov drivers (krylov.cu)
 
@@ -373,12 +395,20 @@ struct KrylovOps {
 	/// out[i] = a[i].b[i], i < nd, summed over all ranks, returned on the host; the return value
 	/// points to the same results in device memory (valid until the next call)
 	virtual const double *dots(int nd, const double *const *a, const double *const *b, double *out) = 0;
+	/// the same without the hand-over to the host: launches (and all-reduces) only, result on the
+	/// device, valid until the next dots call; no host synchronisation
+	virtual const double *dots_device(int nd, const double *const *a, const double *const *b) = 0;
 	/// Basis storage for the restarted solvers.  Taken from a buffer that outlives the solve (the
 	/// operator's) when there is one: allocating and freeing gigabytes inside every solve costs
 	/// tens of milliseconds of idle GPU.
 	KrylovStore *ws = nullptr;
 	KrylovStore own_ws;
-	double *work_vec(int i) { return (ws ? *ws : own_ws).vec(n, i); }
+	double *work_vec(int i) { return (ws ? *ws : own_ws).vec(n, i, stream); }
+	/// true if prec() sweeps in place on what its output vector holds on entry (chaotic GS, SGS
+	/// without an initial guess): the drivers then zero that vector before its first use in a solve
+	virtual bool prec_reads_output() const { return false; }
+	/// raises if the preconditioner recorded a failed exact substitution since the last check
+	virtual void check_prec() {}
 };
 
 void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, double *d_x,

@@ -130,12 +130,17 @@ static bool halo_exchange(DistMat& D, const double *x)
 	B200_CUDA(cudaEventRecord(D.ev_packed, D.stream));
 	B200_CUDA(cudaStreamWaitEvent(st, D.ev_packed, 0));
 	B200_NCCL(g_nccl.GroupStart());
-	size_t so = 0, ro = 0;
-	for(size_t k = 0; k < D.neigh.size(); k++) {
-		const size_t ns = (size_t)D.send_count[k]*D.bs, nr = (size_t)D.recv_count[k]*D.bs;
-		if(ns) B200_NCCL(g_nccl.Send(D.send_buf.p + so, ns, ncclFloat64, D.neigh[k], D.comm->comm, st));
-		if(nr) B200_NCCL(g_nccl.Recv(D.halo.p + ro, nr, ncclFloat64, D.neigh[k], D.comm->comm, st));
-		so += ns; ro += nr;
+	try {
+		size_t so = 0, ro = 0;
+		for(size_t k = 0; k < D.neigh.size(); k++) {
+			const size_t ns = (size_t)D.send_count[k]*D.bs, nr = (size_t)D.recv_count[k]*D.bs;
+			if(ns) B200_NCCL(g_nccl.Send(D.send_buf.p + so, ns, ncclFloat64, D.neigh[k], D.comm->comm, st));
+			if(nr) B200_NCCL(g_nccl.Recv(D.halo.p + ro, nr, ncclFloat64, D.neigh[k], D.comm->comm, st));
+			so += ns; ro += nr;
+		}
+	} catch(...) {
+		g_nccl.GroupEnd();                 // never leave the group open behind an exception
+		throw;
 	}
 	B200_NCCL(g_nccl.GroupEnd());
 	B200_CUDA(cudaEventRecord(D.ev_halo, st));
@@ -160,6 +165,9 @@ struct DistOps : public KrylovOps {
 	DistOps(DistMat *D_, Prec *M_) : D(D_), M(M_) {
 		n = D->diag->dim();
 		stream = D->stream;
+		if(D->diag->stream != D->stream || (M && M->stream != D->stream))
+			throw Error("dist solve: the matrix, the partitioned operator and the preconditioner "
+			            "must share one stream");
 		ws = &D->diag->krylov_ws;
 		partial.alloc((size_t)MAX_DOTS*DOT_BLOCKS);
 		dout.alloc(MAX_KRYLOV_DOTS);
@@ -173,15 +181,21 @@ struct DistOps : public KrylovOps {
 		else B200_CUDA(cudaMemcpyAsync(z, r, n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
 	}
 	const double *dots(int nd, const double *const *a, const double *const *b, double *out) override {
+		const double *d = dots_device(nd, a, b);
+		B200_CUDA(cudaMemcpyAsync(out, d, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
+		B200_CUDA(cudaStreamSynchronize(stream));
+		return d;
+	}
+	const double *dots_device(int nd, const double *const *a, const double *const *b) override {
 		if(nd > MAX_KRYLOV_DOTS) throw Error("dots: too many products");
 		for(int o = 0; o < nd; o += MAX_DOTS)
 			launch_multi_dot(n, std::min(MAX_DOTS, nd - o), a + o, b + o, partial, dout.p + o, stream);
 		if(D->comm->world > 1)
 			B200_NCCL(g_nccl.AllReduce(dout.p, dout.p, nd, ncclFloat64, ncclSum, D->comm->comm, stream));
-		B200_CUDA(cudaMemcpyAsync(out, dout.p, nd*sizeof(double), cudaMemcpyDeviceToHost, stream));
-		B200_CUDA(cudaStreamSynchronize(stream));
 		return dout.p;
 	}
+	bool prec_reads_output() const override { return M && prec_sweeps_in_place(*M); }
+	void check_prec() override { if(M) prec_check(*M); }
 };
 
 static thread_local std::string g_derr;
@@ -217,12 +231,12 @@ int b200_comm_unique_id(char id[128])
 int b200_comm_create(const char id[128], int rank, int world, b200_comm **out)
 {
 	return dguarded([&] {
+		b200_comm *h = new b200_comm;
+		h->c.rank = rank; h->c.world = world;
+		if(world == 1) { *out = h; return; }          // a single subdomain never communicates: no NCCL
 		nccl_load(nullptr);
 		ncclUniqueId u;
 		std::memcpy(u.internal, id, 128);
-		b200_comm *h = new b200_comm;
-		h->c.rank = rank; h->c.world = world;
-		if(world == 1) { *out = h; return; }          // a single subdomain never communicates
 		ncclResult_t r = g_nccl.CommInitRank(&h->c.comm, world, u, rank);
 		if(r != ncclSuccess) { delete h; throw Error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
 		*out = h;

@@ -229,7 +229,7 @@ __device__ __forceinline__ bool row_differs(const double *blk, const int r, cons
 	BlkIO<BS>::load_row_ordered(blk, r, cur);        // must precede the overwrite that follows
 	bool ch = false;
 #pragma unroll
-	for(int c = 0; c < BS; c++) ch |= (cur[c] != v[c]);
+	for(int c = 0; c < BS; c++) ch |= (__double_as_longlong(cur[c]) != __double_as_longlong(v[c]));   // bitwise: NaN == NaN
 	return ch;
 }
 

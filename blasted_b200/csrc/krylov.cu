@@ -130,6 +130,12 @@ void gcr(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, in
 	std::vector<double*> p(nrestart, nullptr), q(nrestart, nullptr);
 	auto need = [&](int i) { if(!p[i]) { p[i] = ops.work_vec(2 + 2*i); q[i] = ops.work_vec(3 + 2*i); } };
 	need(0);
+	if(ops.prec_reads_output()) {
+		// the reference's work vectors are value-initialised (tests/solvers.cpp:264-270); a
+		// preconditioner that sweeps in place must not start from what an earlier solve left
+		B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
+		B200_CUDA(cudaMemsetAsync(p[0], 0, n*sizeof(double), st));
+	}
 	std::vector<double> qq(nrestart, 0.0), beta(nrestart, 0.0);
 
 	const double bnorm = std::sqrt(dot1(ops, b, b));
@@ -186,12 +192,29 @@ void gcr(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, in
 	info->bnorm = bnorm;
 }
 
+/// Pinned host buffer (the Hessenberg columns travel through it without a pageable staging copy)
+struct PinnedBuf {
+	double *p = nullptr;
+	explicit PinnedBuf(size_t n) { B200_CUDA(cudaMallocHost((void**)&p, std::max<size_t>(n, 1)*sizeof(double))); }
+	~PinnedBuf() { if(p) cudaFreeHost(p); }
+	PinnedBuf(const PinnedBuf&) = delete;
+	PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
+
 /// Flexible GMRES(m): right preconditioning with a preconditioner that may change between
 /// applications (what an asynchronous sweep is), classical Gram-Schmidt with one fused multi-dot
-/// and one fused multi-axpy per iteration (PETSc's -ksp_type fgmres default), Givens rotations on
+/// and one fused update per iteration (PETSc's -ksp_type fgmres default), Givens rotations on
 /// the host.  In exact arithmetic its iterates coincide with GCR's (tests/solvers.hpp:108-110) at
 /// about half the orthogonalisation traffic: only the Krylov basis V is orthogonalised, the
 /// preconditioned vectors Z are kept for the solution update.
+///
+/// The host is NOT in the iteration: the Gram-Schmidt coefficients stay on the device (the update
+/// reads them there), a one-thread kernel turns them into the Hessenberg column and the
+/// reciprocal norm of the new basis vector, and iterations are enqueued back to back.  Columns are
+/// handed to the host a few iterations at a time (one copy + one synchronisation per hand-over;
+/// the interval follows the observed convergence rate), where the rotations and the convergence
+/// test run; iterations enqueued past the converged one are simply not used.  With eight ranks
+/// this removes the all-ranks-drain-their-queues point that every iteration used to end in.
 void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter, int m,
             b200_solve_info *info)
 {
@@ -200,22 +223,66 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 	if(m < 1) throw Error("FGMRES: restart length must be positive");
 	if(m + 1 > MAX_KRYLOV_DOTS)
 		throw Error("FGMRES: restart length above " + std::to_string(MAX_KRYLOV_DOTS - 1) + " not supported");
+	static const bool every_iteration = getenv("B200_FGMRES_SYNC") != nullptr;   // A/B switch (development)
+	const bool zero_z = ops.prec_reads_output();
 	// basis vectors come from the operator's store as they are first needed (w, v_0, z_0, v_1, ...)
 	double *const w = ops.work_vec(0);
 	std::vector<double*> V(m+1, nullptr), Z(m, nullptr);
 	auto need = [&](int i) {
 		if(!V[i]) V[i] = ops.work_vec(1 + 2*i);
-		if(i < m && !Z[i]) Z[i] = ops.work_vec(2 + 2*i);
+		if(i < m && !Z[i]) {
+			Z[i] = ops.work_vec(2 + 2*i);
+			// a preconditioner that sweeps in place starts from zero, as on the reference's
+			// value-initialised vectors (tests/solvers.cpp:264-270), not from a previous solve
+			if(zero_z) B200_CUDA(cudaMemsetAsync(Z[i], 0, n*sizeof(double), st));
+		}
 	};
 	need(0);
+	const int HS = m + 2;                    // column stride: h_0..h_j, slot m: h_{j+1,j}, slot m+1: flag
 	std::vector<double> H((size_t)(m+1)*m, 0.0), cs(m), sn(m), g(m+1), y(m);
-	DevBuf<double> dy;
-	dy.alloc(m);
+	DevBuf<double> dy, dH, dinv;
+	dy.alloc(m); dH.alloc((size_t)m*HS); dinv.alloc(m);
+	PinnedBuf hH((size_t)m*HS);
 
 	const double bnorm = std::sqrt(dot1(ops, b, b));
 	double resnorm = bnorm;
 	int step = 0;
 	bool done = false;
+
+	// iteration j, enqueued only
+	auto enqueue = [&](int j) {
+		need(j+1);
+		ops.prec(V[j], Z[j]);                              // z_j = M_j^-1 v_j
+		ops.spmv(Z[j], w);                                 // w = A z_j
+		const double *aa[MAX_KRYLOV_DOTS], *bb[MAX_KRYLOV_DOTS];
+		for(int i = 0; i <= j; i++) { aa[i] = V[i]; bb[i] = w; }
+		aa[j+1] = w; bb[j+1] = w;
+		const double *dh = ops.dots_device(j + 2, aa, bb);     // h_i = v_i.w, w.w: one reduction
+		launch_fgmres_column(j, dh, dH.p + (size_t)j*HS, m, dinv.p + j, st);
+		int l0 = 0;
+		for(; j + 1 - l0 > 32; l0 += 32)
+			launch_multi_axpy(n, 32, V.data() + l0, dh + l0, w, st, -1.0);
+		// v_{j+1} = (w - sum h_i v_i) / |.|
+		launch_multi_axpy_scaled(n, j + 1 - l0, V.data() + l0, dh + l0, w, V[j+1], dinv.p + j, st, -1.0);
+	};
+	// iteration j with the host in the loop and an explicit norm (after a flagged cancellation)
+	auto careful = [&](int j, double *hcol) {
+		need(j+1);
+		ops.prec(V[j], Z[j]);
+		ops.spmv(Z[j], w);
+		const double *aa[MAX_KRYLOV_DOTS], *bb[MAX_KRYLOV_DOTS];
+		double out[MAX_KRYLOV_DOTS];
+		for(int i = 0; i <= j; i++) { aa[i] = V[i]; bb[i] = w; }
+		const double *dh = ops.dots(j + 1, aa, bb, out);
+		for(int l0 = 0; l0 <= j; l0 += 32)
+			launch_multi_axpy(n, std::min(32, j + 1 - l0), V.data() + l0, dh + l0, w, st, -1.0);
+		const double hn = std::sqrt(dot1(ops, w, w));
+		for(int i = 0; i <= j; i++) hcol[i] = out[i];
+		hcol[m] = hn; hcol[m+1] = 0.0;
+		if(hn > 0) launch_vec_scal(n, 1.0/hn, w, V[j+1], st);
+	};
+
+	int interval = 1;                                      // iterations enqueued per hand-over
 	while(step < maxiter && !done) {
 		ops.gemv3(-1.0, x, 1.0, b, w);                         // r = b - A x
 		const double beta = std::sqrt(dot1(ops, w, w));
@@ -224,50 +291,62 @@ void fgmres(KrylovOps& ops, const double *b, double *x, double tol, int maxiter,
 		launch_vec_scal(n, 1.0/beta, w, V[0], st);
 		std::fill(g.begin(), g.end(), 0.0);
 		g[0] = beta;
-		int j = 0;
-		for(; j < m && step < maxiter; j++) {
-			need(j+1);
-			ops.prec(V[j], Z[j]);                              // z_j = M_j^-1 v_j
-			ops.spmv(Z[j], w);                                 // w = A z_j
-			// classical Gram-Schmidt with ONE reduction per iteration: h_i = v_i . w and w . w in the
-			// same fused multi-dot (one all-reduce, one host synchronisation), w -= sum h_i v_i, and
-			// |w_new|^2 = w.w - sum h_i^2 because V is orthonormal.  When that difference loses
-			// more than four digits to cancellation the norm is computed explicitly instead.
-			double hn;
-			{
-				const double *aa[MAX_KRYLOV_DOTS], *bb[MAX_KRYLOV_DOTS];
-				double out[MAX_KRYLOV_DOTS];
-				for(int i = 0; i <= j; i++) { aa[i] = V[i]; bb[i] = w; }
-				aa[j+1] = w; bb[j+1] = w;
-				const double *dh = ops.dots(j + 2, aa, bb, out);
-				double sumsq = 0;
-				for(int i = 0; i <= j; i++) { H[(size_t)i*m + j] = out[i]; sumsq += out[i]*out[i]; }
-				for(int l0 = 0; l0 <= j; l0 += 32)
-					launch_multi_axpy(n, std::min(32, j + 1 - l0), V.data() + l0, dh + l0, w, st, -1.0);
-				const double ww = out[j+1], hn2 = ww - sumsq;
-				hn = (hn2 > 1e-4*ww) ? std::sqrt(hn2) : std::sqrt(dot1(ops, w, w));
+		int jq = 0;                                        // columns enqueued
+		int j = 0;                                         // columns accepted (rotated) on the host
+		bool cycle_careful = false;
+		while(j < m && step < maxiter && !done) {
+			const int room = std::min(m - j, maxiter - step);
+			const int target = j + std::max(1, std::min(room, every_iteration ? 1 : interval));
+			if(!cycle_careful) {
+				for(; jq < target; jq++) enqueue(jq);
+				B200_CUDA(cudaMemcpyAsync(hH.p + (size_t)j*HS, dH.p + (size_t)j*HS,
+				                          (size_t)(jq - j)*HS*sizeof(double), cudaMemcpyDeviceToHost, st));
+				B200_CUDA(cudaStreamSynchronize(st));
 			}
-			H[(size_t)(j+1)*m + j] = hn;
-			if(hn > 0) launch_vec_scal(n, 1.0/hn, w, V[j+1], st);
-			// Givens rotations on column j
-			for(int i = 0; i < j; i++) {
-				const double t = cs[i]*H[(size_t)i*m + j] + sn[i]*H[(size_t)(i+1)*m + j];
-				H[(size_t)(i+1)*m + j] = -sn[i]*H[(size_t)i*m + j] + cs[i]*H[(size_t)(i+1)*m + j];
-				H[(size_t)i*m + j] = t;
+			const int jend = cycle_careful ? j + 1 : jq;
+			double prev = resnorm;
+			for(; j < jend && !done; j++) {
+				double *hcol = hH.p + (size_t)j*HS;
+				if(cycle_careful) careful(j, hcol);
+				else if(hcol[m+1] != 0.0) {
+					// cancellation in |w|^2 - sum h^2: what was enqueued from here on used a bad
+					// norm; redo this iteration (and the rest of the cycle) with explicit norms
+					cycle_careful = true;
+					careful(j, hcol);
+					jq = j + 1;
+				}
+				for(int i = 0; i <= j; i++) H[(size_t)i*m + j] = hcol[i];
+				const double hn = hcol[m];
+				H[(size_t)(j+1)*m + j] = hn;
+				// Givens rotations on column j
+				for(int i = 0; i < j; i++) {
+					const double t = cs[i]*H[(size_t)i*m + j] + sn[i]*H[(size_t)(i+1)*m + j];
+					H[(size_t)(i+1)*m + j] = -sn[i]*H[(size_t)i*m + j] + cs[i]*H[(size_t)(i+1)*m + j];
+					H[(size_t)i*m + j] = t;
+				}
+				const double a = H[(size_t)j*m + j], c = H[(size_t)(j+1)*m + j];
+				const double d = std::hypot(a, c);
+				cs[j] = d > 0 ? a/d : 1.0;
+				sn[j] = d > 0 ? c/d : 0.0;
+				H[(size_t)j*m + j] = d;
+				H[(size_t)(j+1)*m + j] = 0.0;
+				g[j+1] = -sn[j]*g[j];
+				g[j] = cs[j]*g[j];
+				prev = resnorm;
+				resnorm = std::fabs(g[j+1]);
+				step++;
+				if(resnorm/bnorm < tol || hn == 0.0 || !std::isfinite(resnorm)) done = true;
 			}
-			const double a = H[(size_t)j*m + j], c = H[(size_t)(j+1)*m + j];
-			const double d = std::hypot(a, c);
-			cs[j] = d > 0 ? a/d : 1.0;
-			sn[j] = d > 0 ? c/d : 0.0;
-			H[(size_t)j*m + j] = d;
-			H[(size_t)(j+1)*m + j] = 0.0;
-			g[j+1] = -sn[j]*g[j];
-			g[j] = cs[j]*g[j];
-			resnorm = std::fabs(g[j+1]);
-			step++;
-			if(resnorm/bnorm < tol || hn == 0.0) { j++; done = true; break; }
+			// next hand-over: about 0.7 of the iterations the current rate still needs, 1..10
+			if(!done) {
+				const double rate = (prev > 0) ? resnorm/prev : 1.0;
+				double needit = 10.0;
+				if(rate < 1.0 && rate > 0.0 && resnorm > 0)
+					needit = std::log(tol*bnorm/resnorm)/std::log(rate);
+				interval = (int)std::max(1.0, std::min(10.0, std::ceil(0.7*needit)));
+			}
 		}
-		// y = R^-1 g, x += Z y
+		// y = R^-1 g, x += Z y   (columns enqueued past j are not used)
 		for(int i = j-1; i >= 0; i--) {
 			double t = g[i];
 			for(int k = i+1; k < j; k++) t -= H[(size_t)i*m + k]*y[k];
@@ -302,6 +381,7 @@ void krylov_solve(const std::string& solver, KrylovOps& ops, const double *d_b, 
 	else if(solver == "richardson") richardson(ops, d_b, d_x, tol, maxiter, info);
 	else throw Error("unknown solver '" + solver + "'");
 	info->device_ms = tm.stop();
+	ops.check_prec();          // a failed exact substitution inside the solve is an error, not a result
 }
 
 }  // namespace b200

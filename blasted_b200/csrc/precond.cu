@@ -28,15 +28,9 @@ static void ensure_events(Prec& P)
 	if(!P.ev0) {
 		B200_CUDA(cudaEventCreate(&P.ev0));
 		B200_CUDA(cudaEventCreate(&P.ev1));
+		B200_CUDA(cudaEventCreate(&P.evc0));
+		B200_CUDA(cudaEventCreate(&P.evc1));
 	}
-}
-
-static double elapsed(Prec& P)
-{
-	B200_CUDA(cudaEventSynchronize(P.ev1));
-	float ms = 0;
-	B200_CUDA(cudaEventElapsedTime(&ms, P.ev0, P.ev1));
-	return ms;
 }
 
 // ------------------------------------------------------------------ compute
@@ -57,7 +51,7 @@ void prec_compute(Prec& P, double precinfo[6])
 	if(!P.scratch.p) P.scratch.alloc(8);
 
 	const bool first = !P.computed;
-	B200_CUDA(cudaEventRecord(P.ev0, st));
+	B200_CUDA(cudaEventRecord(P.evc0, st));
 
 	if(P.is_jacobi_family) {
 		// BJacobiSRPreconditioner::compute, solverops_jacobi.cpp:31-48 / scalar_jacobi_setup :141-147
@@ -96,7 +90,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			if(scalar) scalar_ilu0_init(A, P.pl, nullptr, B200_INIT_F_ORIGINAL, P.sf, st);
 			else B200_CUDA(cudaMemcpyAsync(P.ilu, A.vals, (size_t)A.nnzb*A.bs*A.bs*sizeof(double),
 			                               cudaMemcpyDeviceToDevice, st));
-			B200_CUDA(cudaEventRecord(P.ev0, st));      // time the factorisation proper
+			B200_CUDA(cudaEventRecord(P.evc0, st));      // time the factorisation proper
 		}
 		const double *scale = nullptr;
 		if(P.s.scale) {
@@ -154,8 +148,12 @@ void prec_compute(Prec& P, double precinfo[6])
 		}
 		else if(P.s.nbuildsweeps > 0) {
 			// exact factorisation: iterate to the bitwise fixed point
+			// Every sweep makes at least one more dependency level final (an entry is a deterministic
+			// function of final inputs once its row's predecessors are final), so nlevels sweeps reach
+			// the fixed point; entries are compared bitwise, so a NaN (singular pivot) cannot keep
+			// the loop alive.  Not converging within that bound is an error, not a result.
 			int changed = 1, sw = 0;
-			const int maxsw = A.nbrows*2 + 16;
+			const int maxsw = P.levels.nlevels + 8;
 			while(changed && sw < maxsw) {
 				B200_CUDA(cudaMemsetAsync(P.flag, 0, sizeof(int), st));
 				for(int rep = 0; rep < 4; rep++, sw++) sweep(sw, P.flag);
@@ -163,6 +161,9 @@ void prec_compute(Prec& P, double precinfo[6])
 				B200_CUDA(cudaStreamSynchronize(st));
 			}
 			P.factor_sweeps_done = sw;
+			if(changed)
+				throw Error("exact ILU(0) factorisation did not reach its fixed point within " +
+				            std::to_string(sw) + " sweeps (" + std::to_string(P.levels.nlevels) + " levels)");
 		}
 
 		if(info && precinfo) {
@@ -188,9 +189,24 @@ void prec_compute(Prec& P, double precinfo[6])
 	}
 	else throw Error("Invalid preconditioner!");
 
-	B200_CUDA(cudaEventRecord(P.ev1, st));
-	P.compute_ms = elapsed(P);
+	// asynchronous: the elapsed time is read when somebody asks (b200_prec_last_times)
+	B200_CUDA(cudaEventRecord(P.evc1, st));
+	P.compute_timed = true;
 	P.computed = true;
+}
+
+// ------------------------------------------------------------------ deferred errors
+
+void prec_check(Prec& P)
+{
+	if(!P.sync_flags.p) return;
+	int flag = 0;
+	B200_CUDA(cudaMemcpyAsync(&flag, P.sync_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, P.stream));
+	B200_CUDA(cudaStreamSynchronize(P.stream));
+	if(flag) {
+		B200_CUDA(cudaMemsetAsync(P.sync_flags.p + 1, 0, sizeof(int), P.stream));
+		throw Error("exact substitution did not complete: a dependency never arrived");
+	}
 }
 
 // ------------------------------------------------------------------ level-scheduled sweeps
@@ -285,9 +301,8 @@ static void exact_pair(Prec& P, TriKind lower, TriKind upper, TriArgs aL, TriArg
 	aL.row_begin = aU.row_begin = 0; aL.row_end = aU.row_end = n;
 	aL.rhs = r; aL.x = P.ytemp; aL.descending = false;
 	aU.rhs = P.ytemp; aU.x = z; aU.descending = true;
-	// a failure of an earlier call was reported then (b200_prec_apply_host) or is the caller's to
-	// fetch; start clean so that one bad call does not poison the object
-	B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), P.stream));
+	// the error flag is sticky: it is cleared only by whoever reads and reports it (prec_check: the
+	// *_host entry points, the Krylov drivers, b200_prec_check); the ticket is reset per launch
 	double *zz = z;
 	if(z == r) {                       // in-place call: the upper solve may not overwrite r early
 		if(!P.lev_z.p) { P.lev_r.alloc(P.A->dim()); P.lev_z.alloc(P.A->dim()); }

@@ -114,7 +114,7 @@ scalar_lower_kernel(const long long n, const int4 *__restrict__ lmeta,
 			if(MODE == SM_RESIDUAL) res += fabs(sm - old[u]*ujj[u]);
 			else {
 				const double out = sm/ujj[u];
-				if(changed && old[u] != out) *changed = 1;
+				if(changed && __double_as_longlong(old[u]) != __double_as_longlong(out)) *changed = 1;   // bitwise
 				lval[t] = out;                            // single final store
 			}
 		}
@@ -171,7 +171,7 @@ scalar_upper_kernel(const long long n, const int4 *__restrict__ ulist,
 			}
 			if(MODE == SM_RESIDUAL) res += fabs(sm - ld_iter(dst));
 			else {
-				if(changed && ld_iter(dst) != sm) *changed = 1;
+				if(changed && __double_as_longlong(ld_iter(dst)) != __double_as_longlong(sm)) *changed = 1;
 				*dst = sm;
 			}
 		}

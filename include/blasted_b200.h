@@ -65,7 +65,9 @@ typedef struct b200_settings {
 	int bs;                   /* block size: 1, 4 or 5 (preconditioners); SpMV also 3 and 7 */
 	int blockstorage;         /* b200_block_storage */
 	int relax;                /* request relaxation instead of preconditioning */
-	int thread_chunk_size;    /* (block-)rows per CTA hint; <= 0 selects the default */
+	int thread_chunk_size;    /* accepted for interface parity and IGNORED: the OpenMP dynamic-schedule
+	                           * chunk of the reference (solverfactory.hpp:55) has no device counterpart -
+	                           * work is mapped by persistent grids sized from the SM count */
 	int scale;                /* symmetric scaling of the matrix before ILU */
 	int nbuildsweeps;         /* asynchronous factorisation sweeps */
 	int napplysweeps;         /* asynchronous triangular-solve / SGS sweeps */
@@ -188,6 +190,13 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z);
 int b200_prec_set_apply_params(b200_prec *p, double rtol, double atol, double dtol, int ctol, int maxits);
 int b200_prec_apply_relax(b200_prec *p, const double *d_b, double *d_x, int maxits);
 int b200_prec_apply_relax_host(b200_prec *p, const double *b, double *x, int maxits);
+/** Deferred errors of the asynchronous device-pointer entry points: synchronises the handle's
+ *  stream and fails (once) if a one-launch exact substitution (seqilu0 / sapilu0 / level types)
+ *  met a dependency that never arrived since the last check.  The *_host entry points and the
+ *  Krylov drivers call it themselves; callers of b200_prec_apply() call it where they next
+ *  synchronise (the reference throws synchronously from apply(); there is no asynchronous
+ *  counterpart in include/solverops_base.hpp). */
+int b200_prec_check(b200_prec *p);
 int b200_prec_dim(const b200_prec *p);
 int b200_prec_relaxation_available(const b200_prec *p);
 void b200_prec_destroy(b200_prec *p);

@@ -18,6 +18,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libblasted_ref.so")
+# the product's C++ adapters behind the reference's handles (tests only; loads libblasted_b200.so)
+ADAPTER_SO = os.path.join(_HERE, "_ref", "libb200_adapters.so")
 
 INIT_F = {"init_zero": 0, "init_original": 1, "init_sgs": 2, "init_none": 3}
 INIT_A = {"init_zero": 0, "init_jacobi": 1, "init_none": 2}
@@ -311,7 +313,7 @@ class RefPrec:
                  fact_init="init_original", apply_init="init_jacobi", thread_chunk_size=128,
                  compute_precinfo=False, through_b200_factory=False):
         self.lib, self.m = lib, m
-        create = lib.ref_prec_create_b200 if through_b200_factory else lib.ref_prec_create
+        create = through_b200_factory if through_b200_factory else lib.ref_prec_create
         self.h = create(prectype.encode(), m.bs, int(m.rowmajor), int(scale),
                                      nbuildsweeps, napplysweeps, INIT_F[fact_init],
                                      INIT_A[apply_init], thread_chunk_size, int(compute_precinfo),
@@ -370,13 +372,13 @@ class _Ref:
     """Wrapper over the unmodified reference build (oracle/_ref/libblasted_ref.so)."""
 
     def __init__(self):
-        L = self.lib = C.CDLL(REF_SO)
+        # RTLD_GLOBAL: libb200_adapters.so (loaded on demand) resolves the reference's classes here
+        L = self.lib = C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)
+        self._adapters = None
         vp = C.c_void_p
         L.ref_last_error.restype = C.c_char_p
         L.ref_prec_create.restype = vp
         L.ref_prec_create.argtypes = [C.c_char_p] + [C.c_int] * 10 + [_ip, _ip, _dp, _ip]
-        L.ref_prec_create_b200.restype = vp
-        L.ref_prec_create_b200.argtypes = L.ref_prec_create.argtypes
         L.ref_prec_compute.argtypes = [vp, _dp]
         L.ref_prec_apply.argtypes = [vp, _dp, _dp]
         L.ref_prec_apply_relax.argtypes = [vp, _dp, _dp, C.c_int]
@@ -407,7 +409,20 @@ class _Ref:
         L.ref_srmat_copy.argtypes = [vp, _ip, _ip, _ip, _dp]
         L.ref_srmat_destroy.argtypes = [vp]
         L.ref_reorder_scale.argtypes = [C.c_int, C.c_int] + [vp] * 8 + [C.c_int, vp, vp]
-        L.ref_reorder_scale_b200.argtypes = L.ref_reorder_scale.argtypes
+
+    def adapters(self):
+        """oracle/_ref/libb200_adapters.so: the product's C++ adapters (blasted_b200/host) behind
+        the handles of this driver.  Loaded only when a test asks for it - the reference arm of
+        bench.py never does, so that process maps nothing of the product."""
+        if self._adapters is None:
+            if not os.path.exists(ADAPTER_SO):
+                raise RuntimeError("oracle/_ref/libb200_adapters.so not built")
+            A = C.CDLL(ADAPTER_SO, mode=C.RTLD_GLOBAL)
+            A.ref_prec_create_b200.restype = C.c_void_p
+            A.ref_prec_create_b200.argtypes = self.lib.ref_prec_create.argtypes
+            A.ref_reorder_scale_b200.argtypes = self.lib.ref_reorder_scale.argtypes
+            self._adapters = A
+        return self._adapters
 
     # ---- front end ----
     def read_mtx(self, path, bs, rowmajor=False):
@@ -435,7 +450,7 @@ class _Ref:
             return None if a is None else np.array(a, dtype=np.float64)
         bp, bc, v, di = m.browptr.copy(), m.bcolind.copy(), m.vals.copy(), m.diagind.copy()
         ro, co, rs, cs, rv, cv = ia(rord), ia(cord), da(rowscale), da(colscale), da(rowvec), da(colvec)
-        fn = self.lib.ref_reorder_scale_b200 if through_b200 else self.lib.ref_reorder_scale
+        fn = self.adapters().ref_reorder_scale_b200 if through_b200 else self.lib.ref_reorder_scale
         rc = fn(m.bs, m.nbrows, _opt(bp), _opt(bc), _opt(v), _opt(di), _opt(ro),
                                         _opt(co), _opt(rs), _opt(cs), int(inverse), _opt(rv), _opt(cv))
         if rc:
@@ -454,7 +469,7 @@ class _Ref:
     def prec_b200(self, m, prectype, **kw) -> RefPrec:
         """The product's device preconditioner created through its C++ B200Factory adapter
         (blasted_b200/host), i.e. behind the reference's own SRPreconditioner interface."""
-        return RefPrec(self.lib, m, prectype, through_b200_factory=True, **kw)
+        return RefPrec(self.lib, m, prectype, through_b200_factory=self.adapters().ref_prec_create_b200, **kw)
 
     def spmv(self, m, x):
         y = np.empty(m.dim)

@@ -5,7 +5,9 @@
  * where they lie under /root/reference (see oracle/Makefile) into oracle/_ref/libblasted_ref.so.
  * It is used (1) to pin the plain-C restatement in oracle/blasted_oracle.c, (2) to generate the
  * golden vectors under tests/golden/, and (3) as the CPU baseline ("kind": "reference") in bench.py.
- * Nothing in the product path (blasted_b200/) links or loads it.
+ * Nothing in the product path (blasted_b200/) links or loads it, and it links nothing of the product:
+ * the entry points that drive the product's C++ adapters live in oracle/adapter_driver.cpp
+ * (oracle/_ref/libb200_adapters.so).
  *
  * It drives the reference exactly the way its own callers do:
  *   - tests/testsolve.cpp:43-88   (matrix views, SRFactory::create_preconditioner, compute)
@@ -32,26 +34,15 @@
 #include "coomatrix.hpp"
 #include "reorderingscaling.hpp"
 #include "../tests/solvers.hpp"
-#include "../blasted_b200/host/b200_solverops.hpp"
+#include "ref_driver_common.hpp"
 
 using namespace blasted;
+using namespace refdrv;
 
 namespace {
 
-typedef SRMatrixStorage<const double, const int> CStorage;
+thread_local std::string g_err;
 
-CStorage wrap(const int nbrows, const int *browptr, const int *bcolind, const double *vals,
-              const int *diagind, const int bs)
-{
-	// same wrapping as src/blasted_petsc.cpp:285-297
-	return CStorage(browptr, bcolind, vals, diagind, browptr+1, nbrows, browptr[nbrows],
-	                browptr[nbrows], bs);
-}
-
-struct RefPrec {
-	SRPreconditioner<double,int> *p;
-	int bs;
-};
 
 // Access to protected factor storage, for parity on intermediate products
 struct ExposeScalarILU : public AsyncILU0_SRPreconditioner<double,int> {
@@ -71,57 +62,13 @@ struct ExposeBJacobi : public BJacobiSRPreconditioner<double,int,bs,stor> {
 	using BJacobiSRPreconditioner<double,int,bs,stor>::dblocks;
 };
 
-thread_local std::string g_err;
-
-// silence the reference's chatter on stdout while a call is in flight
-struct CoutMute {
-	std::streambuf *old;
-	std::ostringstream sink;
-	CoutMute() { old = std::cout.rdbuf(sink.rdbuf()); }
-	~CoutMute() { std::cout.rdbuf(old); }
-};
-
-// front end: the reference's Reordering/ReorderingScaling are abstract (compute() comes from an
-// external ordering package); this subclass only lets the driver set the vectors they apply
-template <int bs>
-struct SetOrderingScaling : public ReorderingScaling<double,int,bs> {
-	void compute(const CRawBSRMatrix<double,int>&) override { }
-	void setScaling(const double *rs, const double *cs, const int n) {
-		if(rs) this->rowscale.assign(rs, rs + n);
-		if(cs) this->colscale.assign(cs, cs + n);
-	}
-};
-
-template <int bs, typename RS = SetOrderingScaling<bs>>
-void ref_reorder_scale(int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
-                       const int *rord, const int *cord, const double *rs, const double *cs,
-                       int inverse, double *rowvec, double *colvec)
-{
-	RS r;
-	r.setOrdering(rord, cord, nbrows);
-	r.setScaling(rs, cs, nbrows);
-	const RSApplyMode mode = inverse ? INVERSE : FORWARD;
-	if(browptr) {
-		RawBSRMatrix<double,int> mat(browptr, bcolind, vals, diagind, browptr+1, nbrows,
-		                             browptr[nbrows], browptr[nbrows]);
-		if(rs || cs) r.applyScaling(mat, mode);
-		if(rord || cord) r.applyOrdering(mat, mode);
-	}
-	if(rowvec) {
-		if(rs) r.applyScaling(rowvec, mode, ROW);
-		if(rord) r.applyOrdering(rowvec, mode, ROW);
-	}
-	if(colvec) {
-		if(cs) r.applyScaling(colvec, mode, COLUMN);
-		if(cord) r.applyOrdering(colvec, mode, COLUMN);
-	}
-}
 
 }
 
 extern "C" {
 
 const char *ref_last_error() { return g_err.c_str(); }
+void ref_set_error(const char *msg) { g_err = msg ? msg : ""; }
 
 int ref_num_threads() { return omp_get_max_threads(); }
 void ref_set_num_threads(int n) { omp_set_num_threads(n); }
@@ -150,40 +97,6 @@ void *ref_prec_create(const char *prectype, int bs, int rowmajor, int scale,
 		RefPrec *h = new RefPrec;
 		h->bs = bs;
 		h->p = fact.create_preconditioner(wrap(nbrows, browptr, bcolind, vals, diagind, bs), s);
-		return h;
-	} catch(std::exception& e) {
-		g_err = e.what();
-		return nullptr;
-	}
-}
-
-/// Same as ref_prec_create but through the product's B200Factory (blasted_b200/host): the returned
-/// object is a device preconditioner behind the reference's SRPreconditioner interface, usable by
-/// every other entry point of this driver (compute/apply/solve with the reference's own Krylov code).
-void *ref_prec_create_b200(const char *prectype, int bs, int rowmajor, int scale,
-                           int nbuildsweeps, int napplysweeps, int fact_init, int apply_init,
-                           int thread_chunk_size, int compute_precinfo,
-                           int nbrows, const int *browptr, const int *bcolind, const double *vals,
-                           const int *diagind)
-{
-	try {
-		blasted_b200::B200Factory fact;
-		AsyncSolverSettings s;
-		s.prectype = fact.solverTypeFromString(prectype);
-		s.bs = bs;
-		s.blockstorage = rowmajor ? RowMajor : ColMajor;
-		s.relax = false;
-		s.thread_chunk_size = thread_chunk_size;
-		s.scale = scale;
-		s.nbuildsweeps = nbuildsweeps;
-		s.napplysweeps = napplysweeps;
-		s.fact_inittype = static_cast<FactInit>(fact_init);
-		s.apply_inittype = static_cast<ApplyInit>(apply_init);
-		s.compute_precinfo = compute_precinfo;
-		RefPrec *h = new RefPrec;
-		h->bs = bs;
-		const FactoryBase<double,int>& f = fact;      // through the abstract factory seam
-		h->p = f.create_preconditioner(wrap(nbrows, browptr, bcolind, vals, diagind, bs), s);
 		return h;
 	} catch(std::exception& e) {
 		g_err = e.what();
@@ -437,22 +350,6 @@ void ref_srmat_copy(void *hh, int *browptr, int *bcolind, int *diagind, double *
 	for(long long i = 0; i < (long long)nz*bs2; i++) vals[i] = h->m.vals[i];
 }
 void ref_srmat_destroy(void *hh) { delete static_cast<RefSRMat*>(hh); }
-
-/// The same through the product's device implementation behind the reference's own interface
-/// (blasted_b200/host: B200ReorderingScaling<bs> : ReorderingScaling<double,int,bs>)
-int ref_reorder_scale_b200(int bs, int nbrows, int *browptr, int *bcolind, double *vals, int *diagind,
-                           const int *rord, const int *cord, const double *rowscale,
-                           const double *colscale, int inverse, double *rowvec, double *colvec)
-{
-	using namespace blasted_b200;
-	try {
-		if(bs == 1) ref_reorder_scale<1,B200ReorderingScaling<1>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
-		else if(bs == 4) ref_reorder_scale<4,B200ReorderingScaling<4>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
-		else if(bs == 7) ref_reorder_scale<7,B200ReorderingScaling<7>>(nbrows, browptr, bcolind, vals, diagind, rord, cord, rowscale, colscale, inverse, rowvec, colvec);
-		else { g_err = "Reordering: only bs 1,4,7 instantiated in the reference"; return 1; }
-	} catch(std::exception& e) { g_err = e.what(); return 1; }
-	return 0;
-}
 
 /// Reordering / ReorderingScaling (src/reorderingscaling.cpp) applied in place to a matrix (may be
 /// null) and to a row-direction and a column-direction vector (may be null).  Scaling is applied
