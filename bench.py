@@ -343,12 +343,20 @@ def run_b200(args):
     # ---- second half of the metric: FGMRES (restarted GCR == FGMRES in exact arithmetic) time to
     # solve, 7-point Poisson n^3 row-partitioned into z-slabs over the ranks (STRONG scaling),
     # block-Jacobi async ILU(0), NCCL halo exchange + all-reduce
-    fgmres = None
+    fgmres, fgmres_ok = None, None
     if args.fgmres_n > 0:
+        # free the headline workload first: the 512^3 operator, its factor and 61 basis vectors
+        # take most of one GPU's HBM
+        del prec, view
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
         try:
             fgmres = run_fgmres(args.fgmres_n, rank, world, dist if world > 1 else None)
-        except Exception as e:                             # reported, never fatal for the headline
-            fgmres = {"error": str(e)[:200]}
+            fgmres_ok = bool(fgmres["converged"]) and fgmres["max_abs_error"] < 1e-3
+        except Exception as e:                             # reported AND reflected in the exit code
+            fgmres = {"error": str(e)[:300]}
+            fgmres_ok = False
 
     if rank != 0:
         if world > 1:
@@ -401,35 +409,44 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "fgmres": fgmres,
+            "fgmres": fgmres, "fgmres_ok": fgmres_ok,
             "algorithmic_bytes_per_step": by["step"],
             "reference_algorithm_bytes_per_step": ref_by["step"],
             "frac_of_peak_whole_step": value/world/peak}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if fgmres_ok is False:
+        sys.exit(3)                                        # a broken solve leg must not look green
 
 
-def run_fgmres(n, rank, world, dist):
+def run_fgmres(n, rank, world, dist, reps=1):
     """Time to solve A x = b (7-point Poisson n^3, x* = 1) to rel. residual 1e-8 with FGMRES(30)
-    preconditioned by per-subdomain async ILU(0) (5 build sweeps, 5 apply sweep pairs; measured fastest in tools/solve_study.py)."""
+    preconditioned by per-subdomain async ILU(0) (5 build sweeps, 5 apply sweep pairs; measured
+    fastest in tools/solve_study.py).  The operator is assembled on the device (z-slab per rank,
+    generator of tests/poisson3d-fd/poisson3d_fd.cpp:108-139 on a uniform grid)."""
     import torch
     import blasted_b200 as bb
     from blasted_b200 import solverfactory as sf
-    from blasted_b200.dist import Comm, DistMatrix, poisson3d_slab
+    from blasted_b200.dist import Comm, DistMatrix, poisson3d_slab_device
 
     comm = Comm.from_torch_distributed() if world > 1 else Comm.single()
-    part = poisson3d_slab(n, rank, world)
-    A = DistMatrix(comm, part)
+    t_setup = time.perf_counter()
+    part, diag_view = poisson3d_slab_device(n, rank, world)
+    A = DistMatrix(comm, part, diag_view)
     s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=5, napplysweeps=5)
     prec = bb.SRFactory().create_preconditioner(A.diag, s)
-    ones = torch.ones(part.diag.dim, dtype=torch.float64, device="cuda")
+    nloc = A.local_dim()
+    ones = torch.ones(nloc, dtype=torch.float64, device="cuda")
     b = A.apply(ones)
     x = torch.zeros_like(b)
     prec.compute()                                         # setup (pattern on device) + warm-up
-    info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=2000, restart=30)
-    best = None
-    for _ in range(2):
+    # warm-up: one full restart cycle touches every basis vector and every kernel of the solve
+    A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=31, restart=30)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    best, info = None, None
+    for _ in range(reps):
         x.zero_()
         torch.cuda.synchronize()
         if dist is not None:
@@ -437,18 +454,25 @@ def run_fgmres(n, rank, world, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         prec.compute()
-        info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=2000, restart=30)
+        info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=6000, restart=30)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         best = float(t.item()) if best is None else min(best, float(t.item()))
-    err = float((x - 1.0).abs().max().item())
+    errt = (x - 1.0).abs().max().reshape(1)
+    if dist is not None:
+        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+    mem = torch.cuda.max_memory_allocated()/2**30
+    free, total = torch.cuda.mem_get_info()
     return {"problem": f"7-point Poisson {n}^3, z-slabs over {world} GPU(s), block-Jacobi async ILU(0) "
                        "(5,5) + FGMRES(30), rel. tol 1e-8", "scaling": "strong",
             "unknowns": n**3, "iterations": info.iters, "converged": bool(info.converged),
-            "time_to_solve_ms": best, "factor_included": True, "max_abs_error": err}
+            "time_to_solve_ms": best, "ms_per_iteration": best/max(info.iters, 1),
+            "factor_included": True, "max_abs_error": float(errt.item()),
+            "timed_solves": reps, "setup_and_warmup_s": t_setup,
+            "hbm_used_gib_rank0": (total - free)/2**30}
 
 
 _STDOUT_FD = None
@@ -480,7 +504,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=1024, help="cells per side (C2 = 1024)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--fgmres-n", type=int, default=256,
+    ap.add_argument("--fgmres-n", type=int, default=512,
                     help="grid size of the FGMRES time-to-solve problem (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

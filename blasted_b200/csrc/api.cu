@@ -622,12 +622,11 @@ int b200_prec_get_factor(b200_prec *p, double *iluvals)
 			download_blocks(A, A.nnzb, tmp, iluvals, P.stream);
 			return;
 		}
-		// reference layout: diagonal blocks hold their inverses (async_blockilu_factor.cpp:144-146)
+		// reference layout: matrix order, diagonal blocks hold their inverses
+		// (async_blockilu_factor.cpp:144-146)
 		DevBuf<double> tmp;
-		const size_t n = (size_t)A.nnzb*A.bs*A.bs;
-		tmp.alloc(n);
-		B200_CUDA(cudaMemcpyAsync(tmp, P.ilu, n*sizeof(double), cudaMemcpyDeviceToDevice, P.stream));
-		launch_scatter_blocks(A, P.dinv, A.diagind, tmp, P.stream);
+		tmp.alloc(std::max<size_t>((size_t)A.nnzb*A.bs*A.bs, 1));
+		block_factor_assemble(A, P.pl, P.sf, P.dinv, tmp, P.stream);
 		download_blocks(A, A.nnzb, tmp, iluvals, P.stream);
 	});
 }
@@ -661,7 +660,7 @@ int b200_prec_ilu_residual(b200_prec *p, double *res)
 		// the residual is defined with UN-inverted diagonal blocks (async_blockilu_factor.cpp:257-297
 		// runs before :144-146), which is how the device keeps the factor
 		*res = (A.bs == 1) ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, P.stream)
-		                   : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, P.stream);
+		                   : ilu0_residual(A, P.pl, scale, P.sf, P.scratch, P.stream);
 	});
 }
 

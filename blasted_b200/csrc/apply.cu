@@ -117,20 +117,28 @@ tri_block_kernel(const TriDev a)
 	if(valid) {
 		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
 		row = a.rows ? __ldg(a.rows + idx) : idx;
-		const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
-		d = __ldg(a.diagind + row);
+		int js, je;
+		const int *cols = a.bcolind;
+		if(a.part_ptr) {
+			// split factor: the part is its own block CSR array, nothing to skip
+			js = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
+			cols = a.part_col;
+			d = -1;
+		} else {
+			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+			d = __ldg(a.diagind + row);
+			part_range<KIND>(s, d, e, js, je);
+		}
 		// everything that depends only on the row is requested before the block loop
 		rhs = __ldg(a.rhs + (size_t)row*BS + r);
 		if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
 		if(KIND != TRI_ILU_LOWER)
 			// compact inverted diagonal blocks: U_ii^-1 (ILU) or D_i^-1 of A (SGS, relaxation)
 			BlkIO<BS>::template load_row<false>(a.dinv + (size_t)row*BS2, r, dr);
-		int js, je;
-		part_range<KIND>(s, d, e, js, je);
 #pragma unroll 2
 		for(int jj = js; jj < je; jj++) {
 			if(KIND == TRI_RELAX && jj == d) continue;
-			const int col = __ldg(a.bcolind + jj);
+			const int col = __ldg(cols + jj);
 			double av[BS], xv[BS];
 			BlkIO<BS>::template load_row<false>(a.vals + (size_t)jj*BS2, r, av);
 			load_seg<BS,true,VEC>(a.xsrc + (size_t)col*BS, xv);
@@ -176,18 +184,24 @@ tri_block_pipe_kernel(const TriDev a)
 	const long long wbase = ((long long)blockIdx.x*wpc + (threadIdx.x >> 5))*GPW;
 	const int nrows = a.row_end - a.row_begin;
 
+	const int *const cols_arr = a.part_ptr ? a.part_col : a.bcolind;
 	auto load_meta = [&](const long long t, int& js, int& je, int& d) {
 		js = 0; je = 0; d = -1;
 		if(g < GPW && t < nrows) {
 			const int row = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
-			const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
-			d = __ldg(a.diagind + row);
-			part_range<KIND>(s, d, e, js, je);
+			if(a.part_ptr) {
+				// split factor: the part is its own block CSR array
+				js = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
+			} else {
+				const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+				d = __ldg(a.diagind + row);
+				part_range<KIND>(s, d, e, js, je);
+			}
 		}
 	};
 	auto load_cols = [&](const int js, const int je, int (&c)[K]) {
 #pragma unroll
-		for(int q = 0; q < K; q++) c[q] = (js + q < je) ? __ldg(a.bcolind + js + q) : 0;
+		for(int q = 0; q < K; q++) c[q] = (js + q < je) ? __ldg(cols_arr + js + q) : 0;
 	};
 
 	int js1, je1, d1, c1[K], js2, je2, d2;
@@ -229,7 +243,7 @@ tri_block_pipe_kernel(const TriDev a)
 			}
 			for(int jj = js + K; jj < je; jj++) {
 				if(KIND == TRI_RELAX && jj == d) continue;
-				const int col = __ldg(a.bcolind + jj);
+				const int col = __ldg(cols_arr + jj);
 				double av[BS], xv[BS];
 				BlkIO<BS>::template load_row<false>(a.vals + (size_t)jj*BS2, r, av);
 				load_seg<BS,true,VEC>(a.xsrc + (size_t)col*BS, xv);
@@ -378,7 +392,7 @@ tri_syncfree_kernel(const TriDev a, int *__restrict__ ticket, int *__restrict__ 
 	if(valid) {
 		const int idx = a.descending ? a.row_end - 1 - (int)t : a.row_begin + (int)t;
 		row = a.rows ? __ldg(a.rows + idx) : idx;
-		if(BS == 1 && a.part_ptr) {
+		if(a.part_ptr) {
 			cbase = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1);
 			cols = a.part_col;
 		} else {

@@ -203,10 +203,18 @@ inline bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31)
 // ------------------------------------------------------------------ cooperative block inverse
 
 /// Inverse of a bs x bs block held one row per lane (lane base + m holds row m in a[]), by
-/// Gauss-Jordan elimination with partial pivoting across the group: pivot search and the pivot
-/// row travel by shuffles, every lane eliminates in its own row.  10 (bs 5) / 8 (bs 4) doubles of
-/// state per lane instead of the bs^2 + 2 bs of the redundant per-lane elimination (solve_right),
-/// which is what lets the factor launches refresh U_ii^-1 themselves without losing a resident CTA.
+/// Gauss-Jordan elimination with partial pivoting across the group: the pivot row travels by
+/// shuffles, every lane eliminates in its own row.  10 (bs 5) / 8 (bs 4) doubles of state per lane
+/// instead of the bs^2 + 2 bs of the redundant per-lane elimination (solve_right), which is what lets
+/// the factor launches refresh U_ii^-1 themselves without losing a resident CTA.
+///
+/// Shuffles share the L1 data pipe with the global loads (ncu on the bs = 5 factor launches:
+/// l1tex__data_pipe_lsu_wavefronts at 81 % of peak, half of it shuffles - a 64-bit shuffle is two
+/// wavefronts), so the exchange is kept minimal: pivot candidates are compared on the high words of
+/// |a_mk| (32-bit shuffles; candidates equal in their upper 32 bits tie, lowest row wins), columns
+/// <= k of the pivot row are not exchanged (they are never read again): 105 (bs 5) shuffle
+/// wavefronts per inverse instead of 160.  (redux.sync + ballot on per-group masks for the pivot
+/// search was measured: 15-35 % SLOWER launches - sub-warp masks serialise.)
 /// On return `inv` holds row `prow` of the inverse (rows end up where their pivots were found).
 /// Must be called by all lanes of the warp; `base` = first lane of the caller's group.
 template <int BS>
@@ -218,25 +226,28 @@ __device__ __forceinline__ void group_inverse(double (&a)[BS], double (&inv)[BS]
 	prow = -1;
 #pragma unroll
 	for(int k = 0; k < BS; k++) {
-		// pivot: largest |a_mk| among the rows not used yet (lowest row on ties, same on every lane)
-		const double mine = (prow < 0) ? fabs(a[k]) : -1.0;
-		double best = -2.0;
-		int bl = 0;
+		// pivot: largest |a_mk| among the rows not used yet, compared on the high words (one
+		// 32-bit shuffle per candidate instead of two); lowest row on ties, same on every lane
+		const int mine = (prow < 0) ? __double2hiint(fabs(a[k])) : -1;
+		int best = -2, bl = 0;
 #pragma unroll
 		for(int m = 0; m < BS; m++) {
-			const double v = __shfl_sync(0xffffffffu, mine, min(base + m, 31));
+			const int v = __shfl_sync(0xffffffffu, mine, min(base + m, 31));
 			if(v > best) { best = v; bl = m; }
 		}
 		const int src = min(base + bl, 31);
+		const bool is_pivot = (base + r == src);
 		const double rinv = 1.0/__shfl_sync(0xffffffffu, a[k], src);
-		const bool is_pivot = (r == bl);
 		const double f = a[k]*rinv;
 #pragma unroll
-		for(int c = 0; c < BS; c++) {
+		for(int c = k + 1; c < BS; c++) {
 			const double pa = __shfl_sync(0xffffffffu, a[c], src);
+			a[c] = is_pivot ? pa*rinv : fma(-f, pa, a[c]);
+		}
+#pragma unroll
+		for(int c = 0; c < BS; c++) {
 			const double pi = __shfl_sync(0xffffffffu, inv[c], src);
-			if(is_pivot) { a[c] = pa*rinv; inv[c] = pi*rinv; }
-			else { a[c] = fma(-f, pa, a[c]); inv[c] = fma(-f, pi, inv[c]); }
+			inv[c] = is_pivot ? pi*rinv : fma(-f, pi, inv[c]);
 		}
 		if(is_pivot) prow = k;
 	}

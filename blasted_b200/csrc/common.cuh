@@ -174,23 +174,21 @@ void vec_scale(long long n, int bs, const double *d_scale, bool inverse, double 
 struct IluPattern {
 	long long npos = 0;
 	DevBuf<int> posptr, lowerp, upperp;  ///< the reference's ILUPositions arrays (bit-identical)
-	// packed per-phase work lists for the block kernels (device-side design, built from the above)
+	// Split form, built from the above (device-side design): strict lower part L, strict upper part
+	// U (CSR each) and the diagonal as separate streams, so that every sweep reads contiguous
+	// arrays, with packed per-phase work lists indexed into them
 	long long nlower = 0, nupper = 0;
-	DevBuf<int2> lmeta;                  ///< per lower entry: {entry, block-column}
-	DevBuf<int4> umeta;                  ///< per upper entry: {entry, pos begin, pos end, row if diagonal else -1}
-	long long nuwork = 0;
-	DevBuf<int4> uwork;                  ///< the subset of umeta that changes between sweeps (has
-	                                     ///< products or is diagonal); the others are U_ij = A_ij
-	DevBuf<int2> pairs;                  ///< {lowerp[k], upperp[k]} interleaved
-	// scalar (bs == 1) split form: strict lower part L, strict upper part U (CSR each) and the
-	// diagonal as separate streams, so that every sweep reads one contiguous array
+	long long nuwork = 0;                ///< upper entries that change between sweeps (have products
+	                                     ///< or are diagonal); the others are U_ij = A_ij
 	long long nstrict = 0;               ///< strict upper entries (= nupper - nbrows)
 	int max_lower_len = 0, max_upper_len = 0;   ///< longest strict lower / strict upper row part
 	DevBuf<int> lptr, lcol, uptr, ucol;
 	DevBuf<int4> slmeta;                 ///< per lower entry: {entry, column, pos begin, pos end}
 	DevBuf<int4> suall, suwork;          ///< per upper entry: {entry, pos begin, pos end, dest};
-	                                     ///< dest = index into the U values, or ~row for a diagonal
-	DevBuf<int2> spairs;                 ///< products re-indexed into the split L / U value arrays
+	                                     ///< dest = index into the U values (blocks: into the
+	                                     ///< column-ordered copy UT), or ~row for a diagonal
+	DevBuf<int2> spairs;                 ///< products re-indexed into the split L / U (blocks: UT) arrays
+	DevBuf<int> ut_order, utpos;         ///< blocks: UT[d] = U[ut_order[d]], utpos = inverse
 	DevBuf<int> lentry, uentry;          ///< split-only build (SGS): position in A of every L / U entry
 	bool built = false, split_built = false;
 };
@@ -202,10 +200,11 @@ void build_split_csr(const Mat& A, IluPattern& pl, cudaStream_t st);
 void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
                          cudaStream_t st);
 
-/// Values of the scalar ILU(0) factor in split form (see IluPattern)
+/// Values of the ILU(0) factor in split form (see IluPattern): scalars, or bs x bs blocks
 struct ScalarFactor {
-	DevBuf<double> lval, uval, udiag;
-	DevBuf<double> alow, aupw;   ///< (scaled) entries of A in lower-list / upper-work-list order
+	DevBuf<double> lval, uval, udiag;   ///< strict lower part, strict upper part (row order), diagonal
+	DevBuf<double> alow, aupw;   ///< scalar: (scaled) entries of A in lower-list / upper-work-list order
+	DevBuf<double> ut;           ///< blocks: strict upper part in column order (factor.cu)
 };
 
 // scalar_ilu.cu
@@ -251,23 +250,30 @@ void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st);
 
 // factor.cu
 void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st);
-/// Block factors: writes the initial guess into `ilu` and (INIT_F_ORIGINAL / INIT_F_SGS, dinv != null)
-/// the inverses of the initial diagonal blocks into the compact array `dinv`.
-void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, double *dinv,
-                      cudaStream_t st);
+/// Block factors live in split form too (factor.cu, "storage").
+void block_factor_alloc(const Mat& A, const IluPattern& pl, ScalarFactor& F);
+/// Writes the initial guess (INIT_F_ORIGINAL / _SGS / _ZERO) into the split arrays.
+void launch_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
+                      ScalarFactor& F, cudaStream_t st);
 /// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
 /// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
 /// `all_upper`: also recompute the upper entries without products (needed once when the initial
 /// guess did not already set them to the scaled A, i.e. for INIT_F_ZERO / INIT_F_NONE).
-void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
                        double *dinv, int *d_changed, bool all_upper, cudaStream_t st);
+/// After the last sweep: the row-order copy of the strict upper part catches up with the
+/// column-order one (entries of the upper work list, or all)
+void launch_sync_upper(const Mat& A, const IluPattern& pl, ScalarFactor& F, bool all, cudaStream_t st);
+/// Factor in the reference's matrix order; diagonal blocks taken from diag_src (U_ii or inverses)
+void block_factor_assemble(const Mat& A, const IluPattern& pl, const ScalarFactor& F,
+                           const double *diag_src, double *out, cudaStream_t st);
 /// dst[positions[i]] <- src[i] for nbrows blocks (copies the compact inverted diagonal blocks into
 /// the factor, the reference's in-place inversion, async_blockilu_factor.cpp:144-146)
 void launch_scatter_blocks(const Mat& A, const double *src_compact, const int *positions, double *dst,
                            cudaStream_t st);
 void launch_invert_diag_blocks(const Mat& A, const double *src_vals, const int *positions_or_null,
                                double *dst, bool dst_is_compact, cudaStream_t st);
-double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,
+double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const ScalarFactor& F,
                      double *d_scratch, cudaStream_t st);
 void diag_dominance(const Mat& A, const double *vals, double out[4], double *d_scratch,
                     cudaStream_t st);
@@ -338,8 +344,8 @@ struct Prec {
 
 	IluPattern pl;
 	Levels levels;
-	DevBuf<double> ilu, scale, ytemp, dinv, xtemp, scratch, dot_partial;
-	ScalarFactor sf;                    ///< bs == 1: the factor lives here (split form), not in `ilu`
+	DevBuf<double> scale, ytemp, dinv, xtemp, scratch, dot_partial;
+	ScalarFactor sf;                    ///< the ILU(0) factor, split form (scalars and blocks)
 	DevBuf<int> flag;
 	DevBuf<double> hr, hz;              ///< staging for *_host entry points
 	bool computed = false;

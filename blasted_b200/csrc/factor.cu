@@ -69,21 +69,87 @@ void launch_scaling_vector(const Mat& A, double *scale, cudaStream_t st)
 
 // (the scalar factorisation lives in scalar_ilu.cu)
 
-enum { PH_ALL = 0, PH_LOWER = 1, PH_UPPER = 2 };
-enum { MODE_SWEEP = 0, MODE_RESIDUAL = 1, MODE_INIT_SGS = 2, MODE_INIT_ORIG = 3 };
+// ------------------------------------------------------------------ block ILU(0): storage
+//
+// The block factor lives in SPLIT form (ScalarFactor, common.cuh): L part `lval` in row order (the
+// order of the lower work list), diagonal blocks U_ii `udiag` (un-inverted; their inverses in the
+// compact array `dinv`), strict upper part `uval` in row order.  Every launch then reads and writes
+// contiguous arrays: the lower launch stores L with unit stride, the triangular sweeps stream
+// their own part instead of skipping over the other one.
+// OPTIONAL second copy `ut` of the strict upper part in COLUMN order (B200_UT=1, bs = 5): the
+// products pair row i of L with column j of U, and for the diagonal entries of a structurally
+// symmetric matrix the two runs are then index-aligned and contiguous.  Only `ut` is kept current
+// during the sweeps in that mode; `uval` catches up once at the end (sync_upper).
 
-// ------------------------------------------------------------------ block ILU(0)
+enum { MODE_INIT_SGS = 2, MODE_INIT_ORIG = 3 };
 
-/// One (partial) asynchronous sweep / residual / initialisation of point-block ILU(0).
+/// Initial guess of point-block ILU(0) written straight into the split arrays.
 /// A group of BS lanes per stored block; lane r holds row r of the block.
-template <int BS, bool SCALE, int PHASE, int MODE>
+template <int BS, bool SCALE, int MODE>
 __global__ void __launch_bounds__(256)
-block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
+block_split_init_kernel(const long long nnzb, const int *__restrict__ browptr,
+                        const int *__restrict__ bcolind, const int *__restrict__ browind,
+                        const int *__restrict__ diagind, const int *__restrict__ lptr,
+                        const int *__restrict__ uptr, const int *__restrict__ utpos,
+                        const double *__restrict__ avals, const double *__restrict__ scale,
+                        double *__restrict__ lval, double *__restrict__ udiag,
+                        double *__restrict__ uval, double *__restrict__ ut)
+{
+	constexpr int GPW = 32/BS;
+	constexpr int BS2 = BS*BS;
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long entry = warp*GPW + g;
+	if(g >= GPW || entry >= nnzb) return;
+	const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
+	const int dg = __ldg(diagind + row);
+	double sum[BS];
+	BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
+	if(SCALE) {
+		// scaleBlock: val(i,j) *= scale[brow*bs+i]*scale[bcol*bs+j]  (kernels_ilu0_factorize.hpp:61-69)
+		const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+	}
+	if(entry < dg) {
+		double *op = lval + ((size_t)__ldg(lptr + row) + (entry - __ldg(browptr + row)))*BS2;
+		if(MODE == MODE_INIT_SGS) {
+			// L' = L D^-1 with D the (scaled) diagonal block of A: async_blockilu_factor.cpp:221-250
+			double d[BS2], x[BS];
+			BlkIO<BS>::template load_full<false>(avals + (size_t)__ldg(diagind + col)*BS2, d);
+			if(SCALE) {
+#pragma unroll
+				for(int c = 0; c < BS; c++)
+#pragma unroll
+					for(int m = 0; m < BS; m++)
+						d[c*BS+m] *= __ldg(scale + (size_t)col*BS + m)*__ldg(scale + (size_t)col*BS + c);
+			}
+			solve_right<BS>(d, sum, x);
+			BlkIO<BS>::store_row(op, r, x);
+		} else
+			BlkIO<BS>::store_row(op, r, sum);
+	}
+	else if(entry == dg)
+		BlkIO<BS>::store_row(udiag + (size_t)row*BS2, r, sum);
+	else {
+		const int ui = __ldg(uptr + row) + (int)(entry - dg - 1);
+		BlkIO<BS>::store_row(uval + (size_t)ui*BS2, r, sum);
+		if(utpos) BlkIO<BS>::store_row(ut + (size_t)__ldg(utpos + ui)*BS2, r, sum);
+	}
+}
+
+/// Nonlinear residual sum |(A - LU)_S| over a factor in MATRIX order with un-inverted diagonal
+/// blocks (assembled from the split form on request; diagnostics only).
+/// A group of BS lanes per stored block; lane r holds row r of the block.
+template <int BS, bool SCALE>
+__global__ void __launch_bounds__(256)
+block_ilu0_residual_kernel(const long long nnzb, const int *__restrict__ bcolind,
                   const int *__restrict__ browind, const int *__restrict__ diagind,
                   const double *__restrict__ avals, const int *__restrict__ posptr,
                   const int *__restrict__ lowerp, const int *__restrict__ upperp,
-                  const double *__restrict__ scale, double *ilu, double *__restrict__ resout,
-                  int *__restrict__ changed, double *__restrict__ dinv_out)
+                  const double *__restrict__ scale, const double *__restrict__ ilu,
+                  double *__restrict__ resout)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
@@ -95,112 +161,94 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 	double sum[BS];
 #pragma unroll
 	for(int c = 0; c < BS; c++) sum[c] = 0;
-	bool active = (g < GPW) && (entry < nnzb);
-	int row = 0, col = 0;
-	bool lower = false;
+	const bool active = (g < GPW) && (entry < nnzb);
 	if(active) {
-		row = __ldg(browind + entry);
-		col = __ldg(bcolind + entry);
-		lower = row > col;
-		if(PHASE == PH_LOWER && !lower) active = false;
-		if(PHASE == PH_UPPER && lower) active = false;
-	}
-	if(active) {
+		const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
+		const bool lower = row > col;
 		BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 		if(SCALE) {
-			// scaleBlock: val(i,j) *= scale[brow*bs+i]*scale[bcol*bs+j]  (kernels_ilu0_factorize.hpp:61-69)
 			const double sr = __ldg(scale + (size_t)row*BS + r);
 #pragma unroll
 			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
 		}
-
-		if(MODE == MODE_SWEEP || MODE == MODE_RESIDUAL) {
-			const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
-			for(int k = ps; k < pe; k++) {
-				double lr[BS], u[BS2];
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)__ldg(lowerp + k)*BS2, r, lr);
-				BlkIO<BS>::template load_full<true>(ilu + (size_t)__ldg(upperp + k)*BS2, u);
-#pragma unroll
-				for(int c = 0; c < BS; c++)
-#pragma unroll
-					for(int m = 0; m < BS; m++)
-						sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
-			}
-		}
-
-		double *op = ilu + (size_t)entry*BS2;
-		if(MODE == MODE_RESIDUAL) {
-			double cur[BS];
-			BlkIO<BS>::template load_row<true>(op, r, cur);
-			if(lower) {
-				double d[BS2];
-				BlkIO<BS>::template load_full<true>(ilu + (size_t)__ldg(diagind + col)*BS2, d);
-#pragma unroll
-				for(int c = 0; c < BS; c++)
-#pragma unroll
-					for(int m = 0; m < BS; m++)
-						sum[c] = fma(-cur[m], d[c*BS+m], sum[c]);
-			} else {
-#pragma unroll
-				for(int c = 0; c < BS; c++) sum[c] -= cur[c];
-			}
-#pragma unroll
-			for(int c = 0; c < BS; c++) res += fabs(sum[c]);
-		}
-		else {
-			if(lower && MODE != MODE_INIT_ORIG) {
-				double d[BS2], x[BS];
-				const size_t dpos = (size_t)__ldg(diagind + col)*BS2;
-				if(MODE == MODE_INIT_SGS) {
-					// D = (scaled) diagonal block of A: async_blockilu_factor.cpp:221-250
-					BlkIO<BS>::template load_full<false>(avals + dpos, d);
-					if(SCALE) {
-#pragma unroll
-						for(int c = 0; c < BS; c++)
-#pragma unroll
-							for(int m = 0; m < BS; m++)
-								d[c*BS+m] *= __ldg(scale + (size_t)col*BS + m)*__ldg(scale + (size_t)col*BS + c);
-					}
-				} else
-					BlkIO<BS>::template load_full<true>(ilu + dpos, d);
-				solve_right<BS>(d, sum, x);
-				BlkIO<BS>::store_row(op, r, x);
-			} else
-				BlkIO<BS>::store_row(op, r, sum);
-		}
-	}
-	if((MODE == MODE_INIT_ORIG || MODE == MODE_INIT_SGS) && dinv_out) {
-		// the initial guess of a diagonal block is the (scaled) A_ii held row-wise in `sum`: invert
-		// it into the compact array right here instead of re-reading it in a separate pass
-		const bool isdiag = active && row == col;
-		if(__any_sync(0xffffffffu, isdiag)) {
-			double d[BS2], e[BS], x[BS];
+		const int ps = __ldg(posptr + entry), pe = __ldg(posptr + entry + 1);
+		for(int k = ps; k < pe; k++) {
+			double lr[BS], u[BS2];
+			BlkIO<BS>::template load_row<false>(ilu + (size_t)__ldg(lowerp + k)*BS2, r, lr);
+			BlkIO<BS>::template load_full<false>(ilu + (size_t)__ldg(upperp + k)*BS2, u);
 #pragma unroll
 			for(int c = 0; c < BS; c++)
 #pragma unroll
 				for(int m = 0; m < BS; m++)
-					d[c*BS+m] = __shfl_sync(0xffffffffu, sum[c], min(g*BS + m, 31));
-			if(isdiag) {
-#pragma unroll
-				for(int c = 0; c < BS; c++) e[c] = (c == r) ? 1.0 : 0.0;
-				solve_right<BS>(d, e, x);
-				BlkIO<BS>::store_row(dinv_out + (size_t)row*BS2, r, x);
-			}
+					sum[c] = fma(-lr[m], u[c*BS+m], sum[c]);
 		}
-	}
-	if(MODE == MODE_RESIDUAL) {
+		double cur[BS];
+		BlkIO<BS>::template load_row<false>(ilu + (size_t)entry*BS2, r, cur);
+		if(lower) {
+			double d[BS2];
+			BlkIO<BS>::template load_full<false>(ilu + (size_t)__ldg(diagind + col)*BS2, d);
 #pragma unroll
-		for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
-		__shared__ double wsum[8];
-		const int w = threadIdx.x >> 5;
-		if(lane == 0) wsum[w] = res;
-		__syncthreads();
-		if(threadIdx.x == 0) {
-			double t = 0;
-			for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
-			atomicAdd(resout, t);
+			for(int c = 0; c < BS; c++)
+#pragma unroll
+				for(int m = 0; m < BS; m++)
+					sum[c] = fma(-cur[m], d[c*BS+m], sum[c]);
+		} else {
+#pragma unroll
+			for(int c = 0; c < BS; c++) sum[c] -= cur[c];
 		}
+#pragma unroll
+		for(int c = 0; c < BS; c++) res += fabs(sum[c]);
 	}
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) res += __shfl_down_sync(0xffffffffu, res, off);
+	__shared__ double wsum[8];
+	const int w = threadIdx.x >> 5;
+	if(lane == 0) wsum[w] = res;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		double t = 0;
+		for(int i = 0; i < (int)(blockDim.x >> 5); i++) t += wsum[i];
+		atomicAdd(resout, t);
+	}
+}
+
+/// out (matrix order) <- split factor; diagonal blocks from `dsrc` (U_ii or their inverses)
+template <int BS>
+__global__ void __launch_bounds__(256)
+block_assemble_kernel(const long long nnzb, const int *__restrict__ browptr,
+                      const int *__restrict__ browind, const int *__restrict__ diagind,
+                      const int *__restrict__ lptr, const int *__restrict__ uptr,
+                      const double *__restrict__ lval, const double *__restrict__ dsrc,
+                      const double *__restrict__ uval, double *__restrict__ out)
+{
+	constexpr int BS2 = BS*BS;
+	const long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(e >= nnzb*BS2) return;
+	const long long entry = e / BS2;
+	const int w = (int)(e - entry*BS2);
+	const int row = browind[entry], dg = diagind[row];
+	double v;
+	if(entry < dg) v = lval[((size_t)lptr[row] + (entry - browptr[row]))*BS2 + w];
+	else if(entry == dg) v = dsrc[(size_t)row*BS2 + w];
+	else v = uval[((size_t)uptr[row] + (entry - dg - 1))*BS2 + w];
+	out[e] = v;
+}
+
+/// uval[ut_order[d]] <- ut[d] for the strict upper entries of `list` (null: all nstrict blocks)
+template <int BS>
+__global__ void __launch_bounds__(256)
+ut_to_uval_kernel(const long long nitems, const int4 *__restrict__ list,
+                  const int *__restrict__ ut_order, const double *__restrict__ ut,
+                  double *__restrict__ uval)
+{
+	constexpr int BS2 = BS*BS;
+	const long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(e >= nitems*BS2) return;
+	const long long t = e / BS2;
+	const int w = (int)(e - t*BS2);
+	int d = (int)t;
+	if(list) { d = list[t].w; if(d < 0) return; }
+	uval[(size_t)ut_order[d]*BS2 + w] = ut[(size_t)d*BS2 + w];
 }
 
 
@@ -214,8 +262,10 @@ block_ilu0_kernel(const long long nnzb, const int *__restrict__ bcolind,
 // Lower entry (i,j), i>j:  L_ij = (A_ij - sum_k L_ik U_kj) U_jj^-1.  U_jj^-1 is read from the compact
 // array `dinv`, which the upper launch of the previous sweep (or the initialisation) wrote from the
 // very U_jj the reference would invert here (kernels_ilu0_factorize.hpp:91); during the lower launch
-// nobody writes U_jj, so the value used is the same.
-// Upper entry (i,j), i<=j: U_ij = A_ij - sum_k L_ik U_kj; a diagonal entry also refreshes dinv[i].
+// nobody writes U_jj, so the value used is the same.  The result goes to lval[t], t the list index:
+// unit-stride stores.
+// Upper entry (i,j), i<=j: U_ij = A_ij - sum_k L_ik U_kj, written to ut (column order) or, for a
+// diagonal entry, to udiag; a diagonal entry also refreshes dinv[i].
 //
 // (A single row-fused launch per sweep - a group walking its block row in column order, as the
 // reference's row kernel does - was measured and dropped: 0.301 ms against 0.118 + 0.173 ms per
@@ -235,11 +285,11 @@ __device__ __forceinline__ bool row_differs(const double *blk, const int r, cons
 
 template <int BS, bool SCALE>
 __global__ void __launch_bounds__(256, 3)
-block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
+block_ilu0_lower_kernel(const long long nlower, const int4 *__restrict__ lmeta,
                         const int *__restrict__ browind, const double *__restrict__ avals,
-                        const int *__restrict__ posptr, const int2 *__restrict__ pairs,
-                        const double *__restrict__ scale, const double *__restrict__ dinv,
-                        double *ilu, int *__restrict__ changed)
+                        const int2 *__restrict__ pairs, const double *__restrict__ scale,
+                        const double *__restrict__ dinv, double *lval, const double *ut,
+                        int *__restrict__ changed)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
@@ -250,47 +300,45 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 	const bool lanevalid = g < GPW;
 
 	// Three-stage software pipeline over this group's items t, t+stride, ...:
-	//   stage M: indices {entry, col} of item i+2        (8 B, from the packed list)
-	//   stage D: data of item i+1 - row r of A_ij, row r of U_jj^-1, the product range
+	//   stage M: {entry, col, product range} of item i+2  (16 B, from the packed list)
+	//   stage D: data of item i+1 - row r of A_ij, row r of U_jj^-1
 	//   stage C: products (rare), L = S * U_jj^-1, single final store of item i
 	// so the loads of the next item are in flight while the current one is computed and stored.
 	// Every lane runs the same instruction stream (the group products are warp collectives);
 	// lanes without an item work on zeros and store nothing.
 	long long t = warp*GPW + g;
-	int2 meta1 = make_int2(-1, -1), meta2 = make_int2(-1, -1);
+	const int4 none = make_int4(-1, -1, 0, 0);
+	int4 meta1 = none, meta2 = none;
 	if(lanevalid && t < nlower) meta1 = __ldg(lmeta + t);
 	if(lanevalid && t + stride < nlower) meta2 = __ldg(lmeta + t + stride);
 
 	double arow[BS], drow[BS];
-	int ps = 0, pe = 0;
 #pragma unroll
 	for(int c = 0; c < BS; c++) { arow[c] = 0; drow[c] = 0; }
 	if(meta1.x >= 0) {
 		BlkIO<BS>::template load_row<false>(avals + (size_t)meta1.x*BS2, r, arow);
 		BlkIO<BS>::template load_row<false>(dinv + (size_t)meta1.y*BS2, r, drow);
-		ps = __ldg(posptr + meta1.x); pe = __ldg(posptr + meta1.x + 1);
 	}
-	int2 meta = meta1;
+	int4 meta = meta1;
 
 	const long long niter = (nlower + stride - 1)/stride;
 	for(long long it = 0; it < niter; it++) {
 		// stage M for item it+2
-		int2 meta3 = make_int2(-1, -1);
+		int4 meta3 = none;
 		if(lanevalid && t + 2*stride < nlower) meta3 = __ldg(lmeta + t + 2*stride);
 		// stage D for item it+1
 		double arow_n[BS], drow_n[BS];
-		int ps_n = 0, pe_n = 0;
 #pragma unroll
 		for(int c = 0; c < BS; c++) { arow_n[c] = 0; drow_n[c] = 0; }
 		if(meta2.x >= 0) {
 			BlkIO<BS>::template load_row<false>(avals + (size_t)meta2.x*BS2, r, arow_n);
 			BlkIO<BS>::template load_row<false>(dinv + (size_t)meta2.y*BS2, r, drow_n);
-			ps_n = __ldg(posptr + meta2.x); pe_n = __ldg(posptr + meta2.x + 1);
 		}
 
 		// stage C for item it
 		const bool active = meta.x >= 0;
 		const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
+		const int ps = meta.z, pe = meta.w;
 		double sum[BS];
 #pragma unroll
 		for(int c = 0; c < BS; c++) sum[c] = arow[c];
@@ -309,15 +357,15 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 #pragma unroll
 			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
 			if(has) {
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
+				BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
 			}
 			group_mul_sub<BS>(sum, lr, ur, g*BS);
 		}
 		double out[BS];
 		group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
 		if(active) {
-			double *op = ilu + (size_t)entry*BS2;
+			double *op = lval + (size_t)t*BS2;
 			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
 			BlkIO<BS>::store_row(op, r, out);                            // single final store
 		}
@@ -326,20 +374,26 @@ block_ilu0_lower_kernel(const long long nlower, const int2 *__restrict__ lmeta,
 		meta = meta2; meta2 = meta3;
 #pragma unroll
 		for(int c = 0; c < BS; c++) { arow[c] = arow_n[c]; drow[c] = drow_n[c]; }
-		ps = ps_n; pe = pe_n;
 		t += stride;
 	}
 }
 
-// The same launch without the data stage of the pipeline: for bs = 5 the second set of row
-// registers costs more in occupancy/spills than the overlap gains.
+// The same launch without the register data stage of the pipeline: for bs = 5 the second set of
+// row registers costs more in occupancy/spills than the overlap gains.  Three resident CTAs: at four
+// (64 registers) the bs = 5 body spills 70 bytes per thread and the spill traffic goes through the
+// very L1 data pipe that bounds the launch - C3 lower launch 0.79 ms at four CTAs, 0.64 ms at three.
+// (Requesting the next item's blocks into L2 one iteration ahead with prefetch.global.L2 was
+// measured as well: 4-11 % SLOWER; the launch is bound by L1 wavefronts, not by DRAM latency.)
+#ifndef B200_L5_MINB
+#define B200_L5_MINB 3
+#endif
 template <int BS, bool SCALE>
-__global__ void __launch_bounds__(256, 4)
-block_ilu0_lower_simple_kernel(const long long nlower, const int2 *__restrict__ lmeta,
+__global__ void __launch_bounds__(256, B200_L5_MINB)
+block_ilu0_lower_simple_kernel(const long long nlower, const int4 *__restrict__ lmeta,
                         const int *__restrict__ browind, const double *__restrict__ avals,
-                        const int *__restrict__ posptr, const int2 *__restrict__ pairs,
-                        const double *__restrict__ scale, const double *__restrict__ dinv,
-                        double *ilu, int *__restrict__ changed)
+                        const int2 *__restrict__ pairs, const double *__restrict__ scale,
+                        const double *__restrict__ dinv, double *lval, const double *ut,
+                        int *__restrict__ changed)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
@@ -350,26 +404,26 @@ block_ilu0_lower_simple_kernel(const long long nlower, const int2 *__restrict__ 
 	const bool lanevalid = g < GPW;
 
 	long long t = warp*GPW + g;
-	int2 meta = make_int2(-1, -1);
+	const int4 none = make_int4(-1, -1, 0, 0);
+	int4 meta = none, metan = none;
 	if(lanevalid && t < nlower) meta = __ldg(lmeta + t);
+	if(lanevalid && t + stride < nlower) metan = __ldg(lmeta + t + stride);
 	const long long niter = (nlower + stride - 1)/stride;
 	for(long long it = 0; it < niter; it++) {
-		const long long tn = t + stride;
-		int2 metan = make_int2(-1, -1);
-		if(lanevalid && tn < nlower) metan = __ldg(lmeta + tn);       // prefetch next item's indices
+		int4 metann = none;
+		if(lanevalid && t + 2*stride < nlower) metann = __ldg(lmeta + t + 2*stride);   // indices two items ahead
 
 		// every lane of the warp runs the same instruction stream (the block exchanges below are
 		// warp collectives); lanes without an item work on zeros and store nothing
 		const bool active = meta.x >= 0;
 		const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
+		const int ps = meta.z, pe = meta.w;
 		double sum[BS], drow[BS];
 #pragma unroll
 		for(int c = 0; c < BS; c++) { sum[c] = 0; drow[c] = 0; }
-		int ps = 0, pe = 0;
 		if(active) {
 			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
 			BlkIO<BS>::template load_row<false>(dinv + (size_t)col*BS2, r, drow);   // row r of U_jj^-1
-			ps = __ldg(posptr + entry); pe = __ldg(posptr + entry + 1);
 		}
 		if(SCALE && active) {
 			const int row = __ldg(browind + entry);
@@ -386,30 +440,30 @@ block_ilu0_lower_simple_kernel(const long long nlower, const int2 *__restrict__ 
 #pragma unroll
 			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
 			if(has) {
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
+				BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
 			}
 			group_mul_sub<BS>(sum, lr, ur, g*BS);
 		}
 		double out[BS];
 		group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
 		if(active) {
-			double *op = ilu + (size_t)entry*BS2;
+			double *op = lval + (size_t)t*BS2;
 			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
 			BlkIO<BS>::store_row(op, r, out);                            // single final store
 		}
-		meta = metan;
-		t = tn;
+		meta = metan; metan = metann;
+		t += stride;
 	}
 }
 
-template <int BS, bool SCALE, bool FUSE_INV>
+template <int BS, bool SCALE>
 __global__ void __launch_bounds__(256, 4)
 block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
                         const int *__restrict__ browind, const int *__restrict__ bcolind,
                         const double *__restrict__ avals, const int2 *__restrict__ pairs,
                         const double *__restrict__ scale, double *__restrict__ dinv,
-                        double *ilu, int *__restrict__ changed)
+                        const double *lval, double *ut, double *udiag, int *__restrict__ changed)
 {
 	constexpr int GPW = 32/BS;
 	constexpr int BS2 = BS*BS;
@@ -420,16 +474,17 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 	const bool lanevalid = g < GPW;
 
 	long long t = warp*GPW + g;
-	int4 meta = make_int4(-1, 0, 0, -1);
+	const int4 none = make_int4(-1, 0, 0, 0);
+	int4 meta = none, metan = none;                       // {entry, pos begin, pos end, dest}
 	if(lanevalid && t < nupper) meta = __ldg(umeta + t);
+	if(lanevalid && t + stride < nupper) metan = __ldg(umeta + t + stride);
 	const long long niter = (nupper + stride - 1)/stride;
 	for(long long it = 0; it < niter; it++) {
-		const long long tn = t + stride;
-		int4 metan = make_int4(-1, 0, 0, -1);
-		if(lanevalid && tn < nupper) metan = __ldg(umeta + tn);
+		int4 metann = none;
+		if(lanevalid && t + 2*stride < nupper) metann = __ldg(umeta + t + 2*stride);
 
 		const bool active = meta.x >= 0;
-		const bool isdiag = active && meta.w >= 0;
+		const bool isdiag = active && meta.w < 0;
 		const int entry = active ? meta.x : 0;
 		double sum[BS];
 #pragma unroll
@@ -443,10 +498,9 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
 			}
 		}
-		// products: warp-uniform trip count, partner blocks exchanged within the group.
-		// (Prefetching the next item's first two product pairs one iteration ahead, so that the
-		// block loads skip the meta -> pair -> block chain, was measured: 0.173 -> 0.1745 ms on C2
-		// and slower for bs = 5 - the launch is bound by the 128-byte gathers, not by that chain.)
+		// products: warp-uniform trip count, partner blocks exchanged within the group.  For a
+		// diagonal entry of a structurally symmetric matrix the pairs are (p, p), (p+1, p+1), ...:
+		// both partners stream.
 		const int ps = active ? meta.y : 0, pe = active ? meta.z : 0;
 		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
 		for(int k = 0; k < nk; k++) {
@@ -457,26 +511,26 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 #pragma unroll
 			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
 			if(has) {
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_row<true>(ilu + (size_t)pr.y*BS2, r, ur);
+				BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
+				BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
 			}
 			group_mul_sub<BS>(sum, lr, ur, g*BS);
 		}
 		if(active) {
-			double *op = ilu + (size_t)entry*BS2;
+			double *op = isdiag ? udiag + (size_t)(~meta.w)*BS2 : ut + (size_t)meta.w*BS2;
 			if(changed && row_differs<BS>(op, r, sum)) *changed = 1;
 			BlkIO<BS>::store_row(op, r, sum);
 		}
-		// a diagonal entry refreshes the compact inverse: every lane of the group gathers the whole
-		// new block (row m lives in lane m) and solves for its own row of the inverse
-		if(FUSE_INV && __any_sync(0xffffffffu, isdiag)) {
+		// a diagonal entry refreshes the compact inverse by the cooperative Gauss-Jordan of
+		// blockops.cuh::group_inverse (row m of the new block lives in lane m)
+		if(__any_sync(0xffffffffu, isdiag)) {
 			double x[BS];
 			int prow;
 			group_inverse<BS>(sum, x, g*BS, r, prow);
-			if(isdiag) BlkIO<BS>::store_row(dinv + (size_t)meta.w*BS2, prow, x);
+			if(isdiag) BlkIO<BS>::store_row(dinv + (size_t)(~meta.w)*BS2, prow, x);
 		}
-		meta = metan;
-		t = tn;
+		meta = metan; metan = metann;
+		t += stride;
 	}
 }
 
@@ -531,26 +585,28 @@ static int persistent_grid(K kernel, long long nitems_per_cta_min, long long nit
 }
 
 template <int BS>
-static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
                                double *dinv, int *changed, bool all_upper, cudaStream_t st)
 {
 	const long long nup = all_upper ? pl.nupper : pl.nuwork;
-	const int4 *uplist = all_upper ? pl.umeta.p : pl.uwork.p;
+	const int4 *uplist = all_upper ? pl.suall.p : pl.suwork.p;
 	constexpr int GPW = 32/BS;
 	const long long per_cta = 8*GPW;
 	static const bool force_simple = getenv("B200_LOWER_SIMPLE") != nullptr;   // A/B switch (development)
 	const bool pipelined = (BS <= 4) && !force_simple;
 	if(pl.nlower > 0) {
 		ProfScope ps(KC_FACTOR_LOWER, st);
+#define B200_LOWER(K)                                                                             \
+		{ auto k = K; k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.slmeta, \
+			A.browind, A.vals, pl.spairs, scale, dinv, F.lval.p, F.ut.p ? F.ut.p : F.uval.p, changed); }
 		if(scale) {
-			auto k = pipelined ? block_ilu0_lower_kernel<BS,true> : block_ilu0_lower_simple_kernel<BS,true>;
-			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
-				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
+			if(pipelined) B200_LOWER((block_ilu0_lower_kernel<BS,true>))
+			else B200_LOWER((block_ilu0_lower_simple_kernel<BS,true>))
 		} else {
-			auto k = pipelined ? block_ilu0_lower_kernel<BS,false> : block_ilu0_lower_simple_kernel<BS,false>;
-			k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.lmeta, A.browind,
-				A.vals, pl.posptr, pl.pairs, scale, dinv, ilu, changed);
+			if(pipelined) B200_LOWER((block_ilu0_lower_kernel<BS,false>))
+			else B200_LOWER((block_ilu0_lower_simple_kernel<BS,false>))
 		}
+#undef B200_LOWER
 		B200_LAUNCHED();
 	}
 	if(nup > 0) {
@@ -560,89 +616,125 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 		// redundant per-lane elimination it replaced cost bs = 4 a resident CTA (80 registers,
 		// 0.173 -> 0.165 ms on C2) and forced bs = 5 into a separate pass over the diagonal
 		// blocks (0.441 -> 0.378 ms on 96^3).
-		constexpr bool FUSE = true;
-		if(scale) {
-			auto k = block_ilu0_upper_kernel<BS,true,FUSE>;
-			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
-				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
-		} else {
-			auto k = block_ilu0_upper_kernel<BS,false,FUSE>;
-			k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,
-				A.bcolind, A.vals, pl.pairs, scale, dinv, ilu, changed);
-		}
+#define B200_UPPER(K)                                                                             \
+		{ auto k = K; k<<<persistent_grid(k, per_cta, nup), 256, 0, st>>>(nup, uplist, A.browind,     \
+			A.bcolind, A.vals, pl.spairs, scale, dinv, F.lval.p, F.ut.p ? F.ut.p : F.uval.p, F.udiag.p, changed); }
+		if(scale) B200_UPPER((block_ilu0_upper_kernel<BS,true>))
+		else B200_UPPER((block_ilu0_upper_kernel<BS,false>))
+#undef B200_UPPER
 		B200_LAUNCHED();
-		if(!FUSE) {
-			constexpr int GPWI = 32/BS;
-			const long long nwarps = ((long long)A.nbrows + GPWI - 1)/GPWI;
-			invert_blocks_kernel<BS><<<div_up(nwarps*32, 256), 256, 0, st>>>(A.nbrows, ilu, A.diagind,
-			                                                             dinv, true);
-			B200_LAUNCHED();
-		}
 	}
 }
 
-template <int BS, int PHASE, int MODE>
-static void launch_block(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
-                         double *resout, int *changed, double *dinv_out, cudaStream_t st)
+static size_t block_count(const Mat& A, long long nblocks) { return (size_t)std::max<long long>(nblocks, 1)*A.bs*A.bs; }
+
+void block_factor_alloc(const Mat& A, const IluPattern& pl, ScalarFactor& F)
+{
+	F.lval.alloc(block_count(A, pl.nlower));
+	F.uval.alloc(block_count(A, pl.nstrict));
+	if(pl.utpos.p) F.ut.alloc(block_count(A, pl.nstrict));      // optional column-order copy
+	F.udiag.alloc(block_count(A, A.nbrows));
+}
+
+template <int BS>
+static void launch_block_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
+                              ScalarFactor& F, cudaStream_t st)
 {
 	constexpr int GPW = 32/BS;
 	const long long nwarps = (A.nnzb + GPW - 1)/GPW;
 	const int grid = div_up(nwarps*32, 256);
-	const int *pp = pl ? pl->posptr.p : nullptr, *lp = pl ? pl->lowerp.p : nullptr,
-		*up = pl ? pl->upperp.p : nullptr;
-	if(scale)
-		block_ilu0_kernel<BS,true,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed, dinv_out);
-	else
-		block_ilu0_kernel<BS,false,PHASE,MODE><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind,
-			A.diagind, A.vals, pp, lp, up, scale, ilu, resout, changed, dinv_out);
+#define B200_INIT(SC, MODE) block_split_init_kernel<BS,SC,MODE><<<grid,256,0,st>>>(A.nnzb, A.browptr, \
+		A.bcolind, A.browind, A.diagind, pl.lptr, pl.uptr, pl.utpos, A.vals, scale, F.lval.p,         \
+		F.udiag.p, F.uval.p, F.ut.p)
+	if(fact_init == B200_INIT_F_SGS) { if(scale) B200_INIT(true, MODE_INIT_SGS); else B200_INIT(false, MODE_INIT_SGS); }
+	else { if(scale) B200_INIT(true, MODE_INIT_ORIG); else B200_INIT(false, MODE_INIT_ORIG); }
+#undef B200_INIT
 	B200_LAUNCHED();
 }
 
-template <int PHASE, int MODE>
-static void launch_any(const Mat& A, const IluPattern *pl, const double *scale, double *ilu,
-                       double *resout, int *changed, cudaStream_t st, double *dinv_out = nullptr)
+void launch_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
+                      ScalarFactor& F, cudaStream_t st)
 {
-	if(A.nnzb == 0) return;
+	if(fact_init == B200_INIT_F_NONE || A.nnzb == 0) return;
+	ProfScope ps(KC_FACTOR_INIT, st);
+	if(fact_init == B200_INIT_F_ZERO) {
+		// the block version really zeroes (async_blockilu_factor.cpp:65-69); the scalar one falls
+		// through into INIT_F_ORIGINAL (async_ilu_factor.cpp:48-54) - both replicated
+		B200_CUDA(cudaMemsetAsync(F.lval, 0, block_count(A, pl.nlower)*sizeof(double), st));
+		B200_CUDA(cudaMemsetAsync(F.uval, 0, block_count(A, pl.nstrict)*sizeof(double), st));
+		if(F.ut.p) B200_CUDA(cudaMemsetAsync(F.ut, 0, block_count(A, pl.nstrict)*sizeof(double), st));
+		B200_CUDA(cudaMemsetAsync(F.udiag, 0, block_count(A, A.nbrows)*sizeof(double), st));
+		return;
+	}
 	switch(A.bs) {
-	case 4: launch_block<4,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
-	case 5: launch_block<5,PHASE,MODE>(A, pl, scale, ilu, resout, changed, dinv_out, st); break;
+	case 4: launch_block_init<4>(A, pl, scale, fact_init, F, st); break;
+	case 5: launch_block_init<5>(A, pl, scale, fact_init, F, st); break;
 	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
 	}
 }
 
-void launch_ilu0_init(const Mat& A, const double *scale, int fact_init, double *ilu, double *dinv,
-                      cudaStream_t st)
-{
-	if(fact_init == B200_INIT_F_NONE) return;
-	ProfScope ps(KC_FACTOR_INIT, st);
-	if(A.bs > 1 && fact_init == B200_INIT_F_ZERO) {
-		// the block version really zeroes (async_blockilu_factor.cpp:65-69); the scalar one falls
-		// through into INIT_F_ORIGINAL (async_ilu_factor.cpp:48-54) - both replicated
-		B200_CUDA(cudaMemsetAsync(ilu, 0, (size_t)A.nnzb*A.bs*A.bs*sizeof(double), st));
-		return;
-	}
-	if(fact_init == B200_INIT_F_SGS)
-		launch_any<PH_ALL,MODE_INIT_SGS>(A, nullptr, scale, ilu, nullptr, nullptr, st, dinv);
-	else
-		launch_any<PH_ALL,MODE_INIT_ORIG>(A, nullptr, scale, ilu, nullptr, nullptr, st, dinv);
-}
-
-void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, double *ilu,
+void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
                        double *dinv, int *d_changed, bool all_upper, cudaStream_t st)
 {
 	if(A.nnzb == 0) return;
-	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, ilu, dinv, d_changed, all_upper, st); return; }
-	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, ilu, dinv, d_changed, all_upper, st); return; }
-	{ ProfScope ps(KC_FACTOR_LOWER, st); launch_any<PH_LOWER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
-	{ ProfScope ps(KC_FACTOR_UPPER, st); launch_any<PH_UPPER,MODE_SWEEP>(A, &pl, scale, ilu, nullptr, d_changed, st); }
+	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, F, dinv, d_changed, all_upper, st); return; }
+	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, F, dinv, d_changed, all_upper, st); return; }
+	throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
 }
 
-double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const double *ilu,
+void launch_sync_upper(const Mat& A, const IluPattern& pl, ScalarFactor& F, bool all, cudaStream_t st)
+{
+	// strict upper entries that the sweeps may have changed: row-order copy <- column-order copy
+	if(!F.ut.p) return;                                               // one copy only: nothing to sync
+	const long long n = all ? pl.nstrict : pl.nuwork - A.nbrows;      // work list = diagonals + entries with products
+	if(n <= 0) return;
+	const long long items = all ? pl.nstrict : pl.nuwork;
+	const int4 *list = all ? nullptr : pl.suwork.p;
+	ProfScope ps(KC_OTHER, st);
+	const int grid = div_up(items*A.bs*A.bs, 256);
+	switch(A.bs) {
+	case 4: ut_to_uval_kernel<4><<<grid,256,0,st>>>(items, list, pl.ut_order, F.ut.p, F.uval.p); break;
+	case 5: ut_to_uval_kernel<5><<<grid,256,0,st>>>(items, list, pl.ut_order, F.ut.p, F.uval.p); break;
+	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+	}
+	B200_LAUNCHED();
+}
+
+void block_factor_assemble(const Mat& A, const IluPattern& pl, const ScalarFactor& F,
+                           const double *diag_src, double *out, cudaStream_t st)
+{
+	if(A.nnzb == 0) return;
+	const int grid = div_up(A.nnzb*A.bs*A.bs, 256);
+	switch(A.bs) {
+	case 4: block_assemble_kernel<4><<<grid,256,0,st>>>(A.nnzb, A.browptr, A.browind, A.diagind, pl.lptr,
+	                                                    pl.uptr, F.lval.p, diag_src, F.uval.p, out); break;
+	case 5: block_assemble_kernel<5><<<grid,256,0,st>>>(A.nnzb, A.browptr, A.browind, A.diagind, pl.lptr,
+	                                                    pl.uptr, F.lval.p, diag_src, F.uval.p, out); break;
+	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+	}
+	B200_LAUNCHED();
+}
+
+double ilu0_residual(const Mat& A, const IluPattern& pl, const double *scale, const ScalarFactor& F,
                      double *d_scratch, cudaStream_t st)
 {
+	if(A.nnzb == 0) return 0.0;
+	// diagnostics only: assembled in matrix order (un-inverted diagonal blocks) for the reference's
+	// own position lists
+	DevBuf<double> tmp;
+	tmp.alloc((size_t)A.nnzb*A.bs*A.bs);
+	block_factor_assemble(A, pl, F, F.udiag.p, tmp, st);
 	B200_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(double), st));
-	launch_any<PH_ALL,MODE_RESIDUAL>(A, &pl, scale, const_cast<double*>(ilu), d_scratch, nullptr, st);
+	const int GPW = 32/A.bs;
+	const long long nwarps = (A.nnzb + GPW - 1)/GPW;
+	const int grid = div_up(nwarps*32, 256);
+#define B200_RES(BSV, SC) block_ilu0_residual_kernel<BSV,SC><<<grid,256,0,st>>>(A.nnzb, A.bcolind, A.browind, \
+		A.diagind, A.vals, pl.posptr, pl.lowerp, pl.upperp, scale, tmp.p, d_scratch)
+	if(A.bs == 4) { if(scale) B200_RES(4, true); else B200_RES(4, false); }
+	else if(A.bs == 5) { if(scale) B200_RES(5, true); else B200_RES(5, false); }
+	else throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+#undef B200_RES
+	B200_LAUNCHED();
 	double r = 0;
 	B200_CUDA(cudaMemcpyAsync(&r, d_scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
 	B200_CUDA(cudaStreamSynchronize(st));

@@ -90,22 +90,6 @@ __global__ void lower_count_kernel(const int n, const int *__restrict__ browptr,
 	else if(i == n) nl_row[i] = 0;
 }
 
-__global__ void __launch_bounds__(256)
-work_lists_kernel(const long long nnzb, const int *__restrict__ browptr,
-                  const int *__restrict__ bcolind, const int *__restrict__ diagind,
-                  const int *__restrict__ browind, const int *__restrict__ posptr,
-                  const int *__restrict__ loff, int2 *__restrict__ lmeta, int4 *__restrict__ umeta)
-{
-	const long long j = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-	if(j >= nnzb) return;
-	const int row = browind[j], col = bcolind[j];
-	const int rs = browptr[row], dg = diagind[row], lo = loff[row];
-	if(j < dg)
-		lmeta[lo + (j - rs)] = make_int2((int)j, col);
-	else
-		umeta[(rs - lo) + (j - dg)] = make_int4((int)j, posptr[j], posptr[j+1], col == row ? row : -1);
-}
-
 __global__ void upper_work_flags_kernel(const long long n, const int4 *__restrict__ umeta,
                                         char *__restrict__ flags, const bool scalar_form)
 {
@@ -172,7 +156,8 @@ __global__ void __launch_bounds__(256)
 scalar_pairs_kernel(const long long npos, const int *__restrict__ lowerp,
                     const int *__restrict__ upperp, const int *__restrict__ rowptr,
                     const int *__restrict__ diagind, const int *__restrict__ rowind,
-                    const int *__restrict__ loff, int2 *__restrict__ spairs)
+                    const int *__restrict__ loff, const int *__restrict__ utpos,
+                    int2 *__restrict__ spairs)
 {
 	const long long k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if(k >= npos) return;
@@ -180,8 +165,27 @@ scalar_pairs_kernel(const long long npos, const int *__restrict__ lowerp,
 	const int rp = rowind[p], rq = rowind[q];
 	const int li = loff[rp] + (p - rowptr[rp]);
 	const int ui = (rowptr[rq] - loff[rq] - rq) + (q - diagind[rq] - 1);
-	spairs[k] = make_int2(li, ui);
+	spairs[k] = make_int2(li, utpos ? utpos[ui] : ui);     // blocks: U partner in column-major storage
 }
+
+/// utpos[ut_order[d]] = d
+__global__ void invert_order_kernel(const long long n, const int *__restrict__ order, int *__restrict__ pos)
+{
+	const long long d = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(d < n) pos[order[d]] = (int)d;
+}
+
+/// blocks: destinations of the strict upper entries move to the column-major copy
+__global__ void upper_dest_transposed_kernel(const long long n, int4 *__restrict__ uall,
+                                             const int *__restrict__ utpos)
+{
+	const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(t >= n) return;
+	int4 m = uall[t];
+	if(m.w >= 0) { m.w = utpos[m.w]; uall[t] = m; }
+}
+
+__global__ void iota_kernel(int n, int *out);
 
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 {
@@ -223,11 +227,10 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.npos = total;
 	pl.lowerp.alloc(std::max<long long>(total, 1));
 	pl.upperp.alloc(std::max<long long>(total, 1));
-	pl.pairs.alloc(A.bs > 1 ? std::max<long long>(total, 1) : 1);
 	if(total > 0) {
 		ilu_positions_kernel<true><<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind,
 		                                                 A.browind, pl.posptr, nullptr, pl.lowerp,
-		                                                 pl.upperp, A.bs > 1 ? pl.pairs.p : nullptr);
+		                                                 pl.upperp, nullptr);
 		B200_LAUNCHED();
 	}
 
@@ -251,10 +254,10 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 		pl.nlower = nl;
 		pl.nupper = nnzb - nl;
 		pl.nstrict = pl.nupper - n;
-		DevBuf<int4> *all_list = &pl.umeta, *work_list = &pl.uwork;
-		if(A.bs == 1) {
-			// scalar: split CSR parts + lists indexed into the split value arrays
-			all_list = &pl.suall; work_list = &pl.suwork;
+		DevBuf<int4> *all_list = &pl.suall, *work_list = &pl.suwork;
+		{
+			// split form (scalars AND blocks): L part, strict U part (CSR each) and lists indexed into
+			// the split value arrays
 			pl.slmeta.alloc(std::max<long long>(pl.nlower, 1));
 			pl.suall.alloc(std::max<long long>(pl.nupper, 1));
 			pl.lcol.alloc(std::max<long long>(pl.nlower, 1));
@@ -278,18 +281,48 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 				B200_CUDA(cudaStreamSynchronize(st));
 				pl.max_lower_len = h[0]; pl.max_upper_len = h[1];
 			}
+			const int *utpos = nullptr;
+			static const bool want_ut = getenv("B200_UT") != nullptr;   // A/B switch (development)
+			if(A.bs == 5 && want_ut) {
+				// OPTIONAL (off: measured no faster while the launches are bound by the L1 data pipe).
+				// Block factors keep a second copy of the strict upper part in COLUMN order (UT): the
+				// U_kj partners of a product then sit next to each other - for a diagonal entry
+				// (i,i) of a structurally symmetric matrix the run UT[column i] is index-aligned with
+				// the run L[row i], so the dominant products stream instead of gathering 200-byte
+				// blocks (measured: isolated 200 B gathers reach 2.2-3.9 TB/s, streams 6.2).
+				// ut_order[d] = row-major strict-upper index of the d-th block in column order (stable
+				// sort by column keeps rows ascending inside a column); utpos is its inverse.
+				pl.ut_order.alloc(std::max<long long>(pl.nstrict, 1));
+				pl.utpos.alloc(std::max<long long>(pl.nstrict, 1));
+				if(pl.nstrict > 0) {
+					DevBuf<int> ids, keys_out;
+					ids.alloc(pl.nstrict); keys_out.alloc(pl.nstrict);
+					iota_kernel<<<div_up(pl.nstrict, 256), 256, 0, st>>>((int)pl.nstrict, ids);
+					B200_LAUNCHED();
+					int bits = 1;
+					while((1LL << bits) < n && bits < 32) bits++;
+					size_t tbs = 0;
+					cub::DeviceRadixSort::SortPairs(nullptr, tbs, pl.ucol.p, keys_out.p, ids.p, pl.ut_order.p,
+					                                (int)pl.nstrict, 0, bits, st);
+					DevBuf<char> tmps;
+					tmps.alloc(tbs);
+					B200_CUDA(cub::DeviceRadixSort::SortPairs(tmps.p, tbs, pl.ucol.p, keys_out.p, ids.p,
+					                                          pl.ut_order.p, (int)pl.nstrict, 0, bits, st));
+					g_launches.fetch_add(1);
+					invert_order_kernel<<<div_up(pl.nstrict, 256), 256, 0, st>>>(pl.nstrict, pl.ut_order, pl.utpos);
+					B200_LAUNCHED();
+					upper_dest_transposed_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, pl.suall, pl.utpos);
+					B200_LAUNCHED();
+					B200_CUDA(cudaStreamSynchronize(st));      // the sort's temporaries go out of scope
+				}
+				utpos = pl.utpos.p;
+			}
 			pl.spairs.alloc(std::max<long long>(total, 1));
 			if(total > 0) {
 				scalar_pairs_kernel<<<div_up(total, 256), 256, 0, st>>>(total, pl.lowerp, pl.upperp,
-					A.browptr, A.diagind, A.browind, loff, pl.spairs);
+					A.browptr, A.diagind, A.browind, loff, utpos, pl.spairs);
 				B200_LAUNCHED();
 			}
-		} else {
-			pl.lmeta.alloc(std::max<long long>(pl.nlower, 1));
-			pl.umeta.alloc(std::max<long long>(pl.nupper, 1));
-			work_lists_kernel<<<grid, 256, 0, st>>>(nnzb, A.browptr, A.bcolind, A.diagind, A.browind,
-			                                        pl.posptr, loff, pl.lmeta, pl.umeta);
-			B200_LAUNCHED();
 		}
 
 		// upper entries that change from sweep to sweep: those with products, and the diagonal
@@ -301,7 +334,7 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 			DevBuf<int> d_nsel;
 			flags.alloc(pl.nupper);
 			d_nsel.alloc(1);
-			upper_work_flags_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, all_list->p, flags, A.bs == 1);
+			upper_work_flags_kernel<<<div_up(pl.nupper, 256), 256, 0, st>>>(pl.nupper, all_list->p, flags, true);
 			B200_LAUNCHED();
 			size_t tb3 = 0;
 			cub::DeviceSelect::Flagged(nullptr, tb3, all_list->p, flags.p, work_list->p, d_nsel.p,

@@ -76,7 +76,6 @@ void prec_compute(Prec& P, double precinfo[6])
 		const bool scalar = (A.bs == 1);       // scalar factors live in split form (P.sf), see scalar_ilu.cu
 		if(first) {
 			// setup_storage + compute_ILU_positions_CSR_CSR on first call: solverops_ilu0.cpp:190-196,358-363
-			if(!scalar) P.ilu.alloc((size_t)A.nnzb*A.bs*A.bs);
 			P.ytemp.alloc(A.dim());
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
 			if(P.s.scale) P.scale.alloc(A.dim());
@@ -88,8 +87,10 @@ void prec_compute(Prec& P, double precinfo[6])
 			// the reference copies A into iluvals at allocation (solverops_ilu0.cpp:160-164,333-337);
 			// this is what INIT_F_NONE then starts from
 			if(scalar) scalar_ilu0_init(A, P.pl, nullptr, B200_INIT_F_ORIGINAL, P.sf, st);
-			else B200_CUDA(cudaMemcpyAsync(P.ilu, A.vals, (size_t)A.nnzb*A.bs*A.bs*sizeof(double),
-			                               cudaMemcpyDeviceToDevice, st));
+			else {
+				block_factor_alloc(A, P.pl, P.sf);
+				launch_ilu0_init(A, P.pl, nullptr, B200_INIT_F_ORIGINAL, P.sf, st);
+			}
 			B200_CUDA(cudaEventRecord(P.evc0, st));      // time the factorisation proper
 		}
 		const double *scale = nullptr;
@@ -108,8 +109,8 @@ void prec_compute(Prec& P, double precinfo[6])
 		else {
 			// (inverting the initial diagonal blocks inside the init launch was measured slower: every
 			// warp then runs the elimination, 322 us against 189 + 74 us for the two passes on C2)
-			launch_ilu0_init(A, scale, P.s.fact_inittype, P.ilu, nullptr, st);
-			launch_invert_diag_blocks(A, P.ilu, A.diagind, dinv, true, st);
+			launch_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
+			launch_invert_diag_blocks(A, P.sf.udiag, nullptr, dinv, true, st);
 		}
 
 		// Async_Level_ILU0 (scalar) passes `threadedfactor`=true into the compute_info slot
@@ -118,7 +119,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			(type == B200_ASYNC_LEVEL_ILU0 && A.bs == 1);
 		if(info && precinfo)
 			precinfo[1] = scalar ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st)
-			                     : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+			                     : ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st);
 
 		// INIT_F_ORIGINAL / INIT_F_SGS already leave U_ij = (scaled) A_ij in every upper entry; the
 		// entries without products never change from that, so only the first sweep after another
@@ -129,7 +130,7 @@ void prec_compute(Prec& P, double precinfo[6])
 		auto sweep = [&](int sw, int *flag) {
 			const bool all_upper = (sw == 0 && !const_upper_set);
 			if(scalar) scalar_ilu0_sweep(A, P.pl, scale, P.sf, flag, all_upper, st);
-			else launch_ilu0_sweep(A, P.pl, scale, P.ilu, dinv, flag, all_upper, st);
+			else launch_ilu0_sweep(A, P.pl, scale, P.sf, dinv, flag, all_upper, st);
 		};
 		if(P.threadedfactor) {
 			for(int sw = 0; sw < P.s.nbuildsweeps; sw++) sweep(sw, nullptr);
@@ -166,17 +167,26 @@ void prec_compute(Prec& P, double precinfo[6])
 				            std::to_string(sw) + " sweeps (" + std::to_string(P.levels.nlevels) + " levels)");
 		}
 
+		// blocks: the sweeps maintain the column-order copy of the strict upper part; the row-order
+		// copy the triangular solves read catches up here (no entries at all for star stencils)
+		if(!scalar && P.factor_sweeps_done > 0 && P.s.nbuildsweeps > 0)
+			launch_sync_upper(A, P.pl, P.sf, !const_upper_set, st);
+
 		if(info && precinfo) {
 			precinfo[0] = scalar ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st)
-			                     : ilu0_residual(A, P.pl, scale, P.ilu, P.scratch, st);
+			                     : ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st);
 			double dd[4];
 			if(scalar) {
 				DevBuf<double> tmp;
 				tmp.alloc(std::max<long long>(A.nnzb, 1));
 				scalar_ilu0_gather(A, P.pl, P.sf, tmp, st);
 				diag_dominance(A, tmp, dd, P.scratch, st);
-			} else
-				diag_dominance(A, P.ilu, dd, P.scratch, st);
+			} else {
+				DevBuf<double> tmp;
+				tmp.alloc((size_t)A.nnzb*A.bs*A.bs);
+				block_factor_assemble(A, P.pl, P.sf, P.sf.udiag, tmp, st);
+				diag_dominance(A, tmp, dd, P.scratch, st);
+			}
 			// PrecInfo layout: [2] upper min, [3] upper avg, [4] lower min, [5] lower avg
 			// (preconditioner_diagnostics.hpp:20-30; arr = {lavg, lmin, uavg, umin})
 			precinfo[5] = dd[0]; precinfo[4] = dd[1]; precinfo[3] = dd[2]; precinfo[2] = dd[3];
@@ -413,15 +423,13 @@ void prec_apply(Prec& P, const double *r, double *z)
 		const double *scale = P.s.scale ? P.scale.p : nullptr;
 		const bool levelled = P.uses_levels || !P.threadedapply;
 		const bool scalar = (A.bs == 1);
-		TriArgs a; a.vals = P.ilu; a.row_begin = 0; a.row_end = A.nbrows;
+		TriArgs a; a.row_begin = 0; a.row_end = A.nbrows;
 		a.dinv = (A.bs > 1) ? P.dinv.p : nullptr;       // compact U_ii^-1 (blocks)
-		// scalar factors are stored split: L part, strict U part, diagonal
+		// factors are stored split: L part, strict U part (each its own CSR / block CSR), diagonal
 		TriArgs aL = a, aU = a;
-		if(scalar) {
-			aL.vals = P.sf.lval; aL.part_ptr = P.pl.lptr; aL.part_col = P.pl.lcol;
-			aU.vals = P.sf.uval; aU.part_ptr = P.pl.uptr; aU.part_col = P.pl.ucol;
-			aU.part_diag = P.sf.udiag;
-		}
+		aL.vals = P.sf.lval; aL.part_ptr = P.pl.lptr; aL.part_col = P.pl.lcol;
+		aU.vals = P.sf.uval; aU.part_ptr = P.pl.uptr; aU.part_col = P.pl.ucol;
+		if(scalar) aU.part_diag = P.sf.udiag;
 		const bool stream = scalar && stream_supported(A.max_row_len);
 		if(levelled) {
 			// Async_Level_ILU0::apply (solverops_levels_ilu0.cpp:58-105,148-192), and the exact

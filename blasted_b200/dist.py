@@ -117,9 +117,13 @@ def poisson3d_slab(n: int, rank: int, world: int, dims=None) -> LocalPart:
     nx, ny, nz = (n, n, n) if dims is None else dims
     zoff = row_offsets(nz, world)
     z0, z1 = int(zoff[rank]), int(zoff[rank+1])
+    return _slab_couplings(nx, ny, z0, z1, rank, world, poisson3d(0, 7, dims=(nx, ny, z1 - z0)))
+
+
+def _slab_couplings(nx, ny, z0, z1, rank, world, diag) -> LocalPart:
+    """Halo plan and off-diagonal block of the z-slab [z0, z1): one plane to each neighbour."""
     plane = nx*ny
-    diag = poisson3d(0, 7, dims=(nx, ny, z1 - z0))
-    nloc = diag.nbrows
+    nloc = plane*(z1 - z0)
     neigh, send_counts, recv_counts, sidx = [], [], [], []
     orow, ocol = [], []
     hoff = 0
@@ -141,6 +145,55 @@ def poisson3d_slab(n: int, rank: int, world: int, dims=None) -> LocalPart:
         offd = SRMatrix(nloc, 1, optr, ocol.astype(np.int32), np.full(len(ocol), -1.0), None)
     return LocalPart(rank, z0*plane, z1*plane, diag, offd, hoff, neigh, send_counts,
                      np.concatenate(sidx) if sidx else np.zeros(0, np.int32), recv_counts)
+
+
+def poisson3d_device(dims, device="cuda", planes_per_chunk: int = 8):
+    """The 7-point Laplacian of matgen.poisson3d(dims=...) assembled ON the device with torch (the
+    512^3 operator has 9.4e8 entries: building it with numpy on the host would take longer than
+    solving with it).  Returns int32 browptr, int32 bcolind, float64 vals as CUDA tensors; same
+    entries in the same order as the host generator (tests/test_gpu_dist.py)."""
+    import torch
+    nx, ny, nz = dims
+    plane = nx*ny
+    n = plane*nz
+    if 7*n >= 2**31:
+        raise ValueError("pattern exceeds int32 indexing")
+    offs = torch.tensor([-plane, -nx, -1, 0, 1, nx, plane], dtype=torch.int64, device=device)
+    counts, cols, diagv = [], [], []
+    for z0 in range(0, nz, planes_per_chunk):
+        z1 = min(nz, z0 + planes_per_chunk)
+        idx = torch.arange(z0*plane, z1*plane, dtype=torch.int64, device=device)
+        x = idx % nx
+        y = (idx // nx) % ny
+        z = idx // plane
+        valid = torch.stack([z > 0, y > 0, x > 0, torch.ones_like(x, dtype=torch.bool),
+                             x < nx - 1, y < ny - 1, z < nz - 1], dim=1)
+        c = idx[:, None] + offs[None, :]
+        counts.append(valid.sum(dim=1, dtype=torch.int32))
+        cols.append(c[valid].to(torch.int32))
+        diagv.append((offs[None, :] == 0).expand_as(valid)[valid])
+    counts = torch.cat(counts)
+    browptr = torch.zeros(n + 1, dtype=torch.int32, device=device)
+    browptr[1:] = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
+    bcolind = torch.cat(cols)
+    del cols
+    isdiag = torch.cat(diagv)
+    vals = torch.where(isdiag, 6.0, -1.0).to(torch.float64)
+    return browptr, bcolind, vals
+
+
+def poisson3d_slab_device(n: int, rank: int, world: int, dims=None):
+    """poisson3d_slab with the diagonal block assembled on the device: returns (part, diag_view)
+    where part.diag is None (no host copy of the big block) and the couplings to the neighbouring
+    slabs (one plane each) are small host arrays as before."""
+    nx, ny, nz = (n, n, n) if dims is None else dims
+    zoff = row_offsets(nz, world)
+    z0, z1 = int(zoff[rank]), int(zoff[rank+1])
+    browptr, bcolind, vals = poisson3d_device((nx, ny, z1 - z0))
+    view = SRMatrixView.from_device(nx*ny*(z1 - z0), 1, browptr, bcolind, vals)
+    del browptr, bcolind, vals
+    part = _slab_couplings(nx, ny, z0, z1, rank, world, None)
+    return part, view
 
 
 # ------------------------------------------------------------------ host-side exchange (tests)
@@ -230,9 +283,9 @@ class Comm:
 class DistMatrix:
     """The rank's share of the partitioned operator on the device."""
 
-    def __init__(self, comm: Comm, part: LocalPart):
+    def __init__(self, comm: Comm, part: LocalPart, diag_view: Optional[SRMatrixView] = None):
         self.comm, self.part = comm, part
-        self.diag = SRMatrixView(part.diag)
+        self.diag = diag_view if diag_view is not None else SRMatrixView(part.diag)
         self.offd = SRMatrixView(part.offd) if part.offd is not None else None
         self._h = C.c_void_p()
         neigh = np.asarray(part.neigh, dtype=np.int32)
@@ -245,7 +298,7 @@ class DistMatrix:
                                        C.byref(self._h)))
 
     def local_dim(self) -> int:
-        return self.part.diag.dim
+        return self.diag.dim()
 
     def apply(self, x, y=None):
         """y_local = (A x)_local; x, y torch CUDA tensors of the local length.  Collective."""

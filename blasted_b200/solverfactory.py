@@ -135,6 +135,25 @@ class SRMatrixView:
                                        m.vals.ctypes.data_as(C.c_void_p), di, C.byref(self._h)))
 
     @classmethod
+    def from_device(cls, nbrows: int, bs: int, browptr, bcolind, vals, rowmajor: bool = False,
+                    keep_host_copy: bool = False) -> "SRMatrixView":
+        """Matrix assembled on the device (torch CUDA tensors: int32 browptr / bcolind, float64
+        vals in the caller's block layout); the arrays are copied, diagonals are located on the
+        device.  No host copy is kept unless asked for (`self.m` is then None)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._bs, self._rowmajor = bs, rowmajor
+        self.m = None
+        import torch
+        assert browptr.dtype == torch.int32 and bcolind.dtype == torch.int32 and vals.dtype == torch.float64
+        check(lib.b200_mat_create_device(nbrows, bs, ROWMAJOR if rowmajor else COLMAJOR,
+                                         C.c_void_p(browptr.data_ptr()), C.c_void_p(bcolind.data_ptr()),
+                                         C.c_void_p(vals.data_ptr()), C.byref(self._h)))
+        if keep_host_copy:
+            self.m = self.to_host()
+        return self
+
+    @classmethod
     def from_handle(cls, handle, bs: int, rowmajor: bool) -> "SRMatrixView":
         """Wraps a matrix that was built on the device (front end); the host copy is fetched."""
         self = cls.__new__(cls)
