@@ -343,11 +343,22 @@ def run_b200(args):
     # ---- second half of the metric: FGMRES (restarted GCR == FGMRES in exact arithmetic) time to
     # solve, 7-point Poisson n^3 row-partitioned into z-slabs over the ranks (STRONG scaling),
     # block-Jacobi async ILU(0), NCCL halo exchange + all-reduce
+    # ---- the other BASELINE configs at their full sizes (N = 1 only): per-kernel rooflines of the
+    # scalar (C1, C4) and bs=5 (C3) paths and of SpMV, so that the driver's record carries them
+    configs = None
+    if world == 1 and not args.no_configs:
+        del prec, view
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        configs = run_configs(peak_hbm())
+
     fgmres, fgmres_ok = None, None
     if args.fgmres_n > 0:
         # free the headline workload first: the 512^3 operator, its factor and 61 basis vectors
         # take most of one GPU's HBM
-        del prec, view
+        if configs is None:
+            del prec, view
         import gc
         gc.collect()
         torch.cuda.empty_cache()
@@ -364,11 +375,7 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel, from the live per-launch CUDA-event times
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = peak_hbm(), peak_hbm_source()
     kernels = {}
     for k in ("factor_lower", "factor_upper", "tri_lower", "tri_upper"):
         tot, cnt = prof[k]
@@ -409,6 +416,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "configs": configs,
             "fgmres": fgmres, "fgmres_ok": fgmres_ok,
             "algorithmic_bytes_per_step": by["step"],
             "reference_algorithm_bytes_per_step": ref_by["step"],
@@ -418,6 +426,56 @@ def run_b200(args):
         dist.destroy_process_group()
     if fgmres_ok is False:
         sys.exit(3)                                        # a broken solve leg must not look green
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+
+
+def peak_hbm_source():
+    return ("measured (MEASURED_PEAKS.json hbm_gbs)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+            else "fallback (B200_PROFILING.md)")
+
+
+def run_configs(peak):
+    """BASELINE.json configs other than the headline, each at its FULL size, assembled on the device:
+    C1 7-point Poisson 256^3 CSR, C3 BSR bs=5 128^3 cells, C4 27-point Poisson 256^3 CSR (scaled
+    factorisation).  Per kernel class: CUDA-event ms per launch, algorithmic bytes per launch
+    (DESIGN.md section 3), achieved GB/s and the fraction of the measured HBM peak - SpMV included
+    (north_star: BSR SpMV >= 60 % of HBM bandwidth).  C2's SpMV is reported with C3's."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config_report as cr
+    out = {}
+    specs = (("C1", "7-point Poisson 256^3 CSR", lambda: cr.device_view(7, (256, 256, 256)), dict(scale=False)),
+             ("C2_spmv", "BSR bs=4 1024x1024 cells (SpMV only)", lambda: cr.device_view("block", (1024, 1024), 4, SEED), None),
+             ("C3", "BSR bs=5 128^3 cells", lambda: cr.device_view("block", (128, 128, 128), 5, SEED + 1), dict(scale=False)),
+             ("C4", "27-point Poisson 256^3 CSR, scaled factorisation", lambda: cr.device_view(27, (256, 256, 256)), dict(scale=True)))
+    for key, desc, make, kw in specs:
+        try:
+            view, (bs, N, nnz) = make()
+            if kw is None:
+                x = torch.randn(N*bs, dtype=torch.float64, device="cuda")
+                y = torch.empty_like(x)
+                ms = cr.timeit(lambda: view.apply(x, y))
+                nbytes = (8*bs*bs + 4)*nnz + 4*(N + 1) + 16*bs*N
+                kern = {"spmv": {"ms": ms, "bytes": int(nbytes), "gbs": nbytes/ms/1e6, "frac": nbytes/ms/1e6/peak}}
+                setup = None
+            else:
+                kern, p, setup, c, _ = cr.measure(view, bs, N, nnz, 3, 3, kw["scale"], steps=3, peak=peak)
+                del p
+            out[key] = {"matrix": desc, "block_rows": N, "nnzb": nnz, "bs": bs, "sweeps": [3, 3],
+                        "first_compute_incl_pattern_build_ms": None if setup is None else setup*1e3,
+                        "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                                    for k, v in kern.items()}}
+            del view
+        except Exception as e:                              # noqa: BLE001 - reported in the line
+            out[key] = {"matrix": desc, "error": str(e)[:300]}
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_fgmres(n, rank, world, dist, reps=1):
@@ -504,6 +562,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=1024, help="cells per side (C2 = 1024)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4 per-kernel block (N = 1)")
     ap.add_argument("--fgmres-n", type=int, default=512,
                     help="grid size of the FGMRES time-to-solve problem (0 = skip)")
     args = ap.parse_args()

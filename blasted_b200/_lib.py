@@ -74,6 +74,7 @@ SYMBOLS = {
     "b200_prec_set_sweeps": (_i, [_vp, _i, _i]),
     "b200_prec_positions_size": (_i, [_vp, C.POINTER(_ll)]),
     "b200_prec_get_positions": (_i, [_vp, _vp, _vp, _vp]),
+    "b200_prec_pattern_stats": (_i, [_vp, _vp]),
     "b200_prec_levels_size": (_i, [_vp, C.POINTER(_i)]),
     "b200_prec_get_levels": (_i, [_vp, _vp, _vp]),
     "b200_prec_get_factor": (_i, [_vp, _vp]),

@@ -571,6 +571,14 @@ int b200_prec_positions_size(b200_prec *p, long long *npos)
 	});
 }
 
+int b200_prec_pattern_stats(b200_prec *p, long long stats[5])
+{
+	return guarded([&] {
+		if(!p->p.pl.built) throw Error("ILU positions not built (not an ILU0 type, or compute() not called)");
+		pattern_stats(p->p.pl, stats, p->p.stream);
+	});
+}
+
 int b200_prec_get_positions(b200_prec *p, int *posptr, int *lowerp, int *upperp)
 {
 	return guarded([&] {

@@ -193,6 +193,7 @@ struct IluPattern {
 	bool built = false, split_built = false;
 };
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
+void pattern_stats(const IluPattern& pl, long long out[5], cudaStream_t st);
 /// Scalar matrices: only the split CSR structure (lptr/lcol/uptr/ucol, lentry/uentry, part lengths),
 /// for sweeps over A itself (SGS); no ILU position lists.
 void build_split_csr(const Mat& A, IluPattern& pl, cudaStream_t st);
@@ -261,6 +262,12 @@ void launch_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, i
 /// guess did not already set them to the scaled A, i.e. for INIT_F_ZERO / INIT_F_NONE).
 void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, ScalarFactor& F,
                        double *dinv, int *d_changed, bool all_upper, cudaStream_t st);
+/// Exact block factorisation in one launch over level-sorted, warp-padded row slots (factor.cu);
+/// rowdone: nbrows ints of scratch, flags: {ticket, error}
+int block_exact_slots(const Mat& A, const Levels& lv, DevBuf<int>& slots, cudaStream_t st);
+void launch_ilu0_exact(const Mat& A, const IluPattern& pl, const int *slots, int nslots,
+                       const double *scale, ScalarFactor& F, double *dinv, int *rowdone, int *flags,
+                       cudaStream_t st);
 /// After the last sweep: the row-order copy of the strict upper part catches up with the
 /// column-order one (entries of the upper work list, or all)
 void launch_sync_upper(const Mat& A, const IluPattern& pl, ScalarFactor& F, bool all, cudaStream_t st);
@@ -364,6 +371,8 @@ struct Prec {
 	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
 	DevBuf<int> sync_flags;                           ///< {ticket, error} of the one-launch exact solves
 	DevBuf<int> rowdone;                              ///< per-row flags of the one-launch exact factorisation
+	DevBuf<int> exact_slots;                          ///< blocks: level-sorted rows, levels padded to whole warps
+	int n_exact_slots = 0;
 
 	int dim() const { return A->nbrows*A->bs; }
 };

@@ -378,7 +378,121 @@ block_ilu0_lower_kernel(const long long nlower, const int4 *__restrict__ lmeta,
 	}
 }
 
-// The same launch without the register data stage of the pipeline: for bs = 5 the second set of
+/// One lower entry: L_ij = (A_ij - sum_k L_ik U_kj) U_jj^-1, single final store to lval[t].
+/// WARP-COLLECTIVE (lanes without an item pass meta.x < 0, work on zeros and store nothing).
+/// FRESH: U_jj^-1 may have been written earlier in THIS launch (one-launch exact factorisation):
+/// read it at L2 instead of through the non-coherent path.
+template <int BS, bool SCALE, bool FRESH>
+__device__ __forceinline__ void lower_item(const int4 meta, const long long t, const int g, const int r,
+                                           const int *__restrict__ browind,
+                                           const double *__restrict__ avals,
+                                           const int2 *__restrict__ pairs,
+                                           const double *__restrict__ scale, const double *dinv,
+                                           double *lval, const double *ut, int *__restrict__ changed)
+{
+	constexpr int BS2 = BS*BS;
+	const bool active = meta.x >= 0;
+	const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
+	const int ps = active ? meta.z : 0, pe = active ? meta.w : 0;
+	double sum[BS], drow[BS];
+#pragma unroll
+	for(int c = 0; c < BS; c++) { sum[c] = 0; drow[c] = 0; }
+	if(active) {
+		BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
+		BlkIO<BS>::template load_row<FRESH>(dinv + (size_t)col*BS2, r, drow);   // row r of U_jj^-1
+	}
+	if(SCALE && active) {
+		const int row = __ldg(browind + entry);
+		const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+	}
+	const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
+	for(int k = 0; k < nk; k++) {
+		const bool has = ps + k < pe;
+		int2 pr = make_int2(0, 0);
+		if(has) pr = __ldg(pairs + ps + k);
+		double lr[BS], ur[BS];
+#pragma unroll
+		for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
+		if(has) {
+			BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
+			BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
+		}
+		group_mul_sub<BS>(sum, lr, ur, g*BS);
+	}
+	double out[BS];
+	group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
+	if(active) {
+		double *op = lval + (size_t)t*BS2;
+		if(changed && row_differs<BS>(op, r, out)) *changed = 1;
+		BlkIO<BS>::store_row(op, r, out);                            // single final store
+	}
+}
+
+/// One upper entry: U_ij = A_ij - sum_k L_ik U_kj, written to ut[dest] or, for a diagonal entry
+/// (dest = ~row), to udiag[row] together with the refreshed inverse dinv[row].  WARP-COLLECTIVE.
+template <int BS, bool SCALE>
+__device__ __forceinline__ void upper_item(const int4 meta, const int g, const int r,
+                                           const int *__restrict__ browind,
+                                           const int *__restrict__ bcolind,
+                                           const double *__restrict__ avals,
+                                           const int2 *__restrict__ pairs,
+                                           const double *__restrict__ scale, double *dinv,
+                                           const double *lval, double *ut, double *udiag,
+                                           int *__restrict__ changed)
+{
+	constexpr int BS2 = BS*BS;
+	const bool active = meta.x >= 0;
+	const bool isdiag = active && meta.w < 0;
+	const int entry = active ? meta.x : 0;
+	double sum[BS];
+#pragma unroll
+	for(int c = 0; c < BS; c++) sum[c] = 0;
+	if(active) {
+		BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
+		if(SCALE) {
+			const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
+			const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
+		}
+	}
+	// products: warp-uniform trip count, partner blocks exchanged within the group.
+	// (Prefetching the next item's first two product pairs one iteration ahead, so that the
+	// block loads skip the meta -> pair -> block chain, was measured: 0.173 -> 0.1745 ms on C2
+	// and slower for bs = 5.)
+	const int ps = active ? meta.y : 0, pe = active ? meta.z : 0;
+	const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
+	for(int k = 0; k < nk; k++) {
+		const bool has = ps + k < pe;
+		int2 pr = make_int2(0, 0);
+		if(has) pr = __ldg(pairs + ps + k);
+		double lr[BS], ur[BS];
+#pragma unroll
+		for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
+		if(has) {
+			BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
+			BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
+		}
+		group_mul_sub<BS>(sum, lr, ur, g*BS);
+	}
+	if(active) {
+		double *op = isdiag ? udiag + (size_t)(~meta.w)*BS2 : ut + (size_t)meta.w*BS2;
+		if(changed && row_differs<BS>(op, r, sum)) *changed = 1;
+		BlkIO<BS>::store_row(op, r, sum);
+	}
+	// a diagonal entry refreshes the compact inverse by the cooperative Gauss-Jordan of
+	// blockops.cuh::group_inverse (row m of the new block lives in lane m)
+	if(__any_sync(0xffffffffu, isdiag)) {
+		double x[BS];
+		int prow;
+		group_inverse<BS>(sum, x, g*BS, r, prow);
+		if(isdiag) BlkIO<BS>::store_row(dinv + (size_t)(~meta.w)*BS2, prow, x);
+	}
+}
+
+// The lower launch without the register data stage of the pipeline: for bs = 5 the second set of
 // row registers costs more in occupancy/spills than the overlap gains.  Three resident CTAs: at four
 // (64 registers) the bs = 5 body spills 70 bytes per thread and the spill traffic goes through the
 // very L1 data pipe that bounds the launch - C3 lower launch 0.79 ms at four CTAs, 0.64 ms at three.
@@ -396,7 +510,6 @@ block_ilu0_lower_simple_kernel(const long long nlower, const int4 *__restrict__ 
                         int *__restrict__ changed)
 {
 	constexpr int GPW = 32/BS;
-	constexpr int BS2 = BS*BS;
 	const int lane = threadIdx.x & 31;
 	const int g = lane / BS, r = lane - g*BS;
 	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -412,46 +525,7 @@ block_ilu0_lower_simple_kernel(const long long nlower, const int4 *__restrict__ 
 	for(long long it = 0; it < niter; it++) {
 		int4 metann = none;
 		if(lanevalid && t + 2*stride < nlower) metann = __ldg(lmeta + t + 2*stride);   // indices two items ahead
-
-		// every lane of the warp runs the same instruction stream (the block exchanges below are
-		// warp collectives); lanes without an item work on zeros and store nothing
-		const bool active = meta.x >= 0;
-		const int entry = active ? meta.x : 0, col = active ? meta.y : 0;
-		const int ps = meta.z, pe = meta.w;
-		double sum[BS], drow[BS];
-#pragma unroll
-		for(int c = 0; c < BS; c++) { sum[c] = 0; drow[c] = 0; }
-		if(active) {
-			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
-			BlkIO<BS>::template load_row<false>(dinv + (size_t)col*BS2, r, drow);   // row r of U_jj^-1
-		}
-		if(SCALE && active) {
-			const int row = __ldg(browind + entry);
-			const double sr = __ldg(scale + (size_t)row*BS + r);
-#pragma unroll
-			for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
-		}
-		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
-		for(int k = 0; k < nk; k++) {
-			const bool has = ps + k < pe;
-			int2 pr = make_int2(0, 0);
-			if(has) pr = __ldg(pairs + ps + k);
-			double lr[BS], ur[BS];
-#pragma unroll
-			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
-			if(has) {
-				BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
-			}
-			group_mul_sub<BS>(sum, lr, ur, g*BS);
-		}
-		double out[BS];
-		group_mul<BS>(out, sum, drow, g*BS);                                 // L = S * U_jj^-1
-		if(active) {
-			double *op = lval + (size_t)t*BS2;
-			if(changed && row_differs<BS>(op, r, out)) *changed = 1;
-			BlkIO<BS>::store_row(op, r, out);                            // single final store
-		}
+		lower_item<BS,SCALE,false>(meta, t, g, r, browind, avals, pairs, scale, dinv, lval, ut, changed);
 		meta = metan; metan = metann;
 		t += stride;
 	}
@@ -466,7 +540,6 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
                         const double *lval, double *ut, double *udiag, int *__restrict__ changed)
 {
 	constexpr int GPW = 32/BS;
-	constexpr int BS2 = BS*BS;
 	const int lane = threadIdx.x & 31;
 	const int g = lane / BS, r = lane - g*BS;
 	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -482,56 +555,98 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 	for(long long it = 0; it < niter; it++) {
 		int4 metann = none;
 		if(lanevalid && t + 2*stride < nupper) metann = __ldg(umeta + t + 2*stride);
-
-		const bool active = meta.x >= 0;
-		const bool isdiag = active && meta.w < 0;
-		const int entry = active ? meta.x : 0;
-		double sum[BS];
-#pragma unroll
-		for(int c = 0; c < BS; c++) sum[c] = 0;
-		if(active) {
-			BlkIO<BS>::template load_row<false>(avals + (size_t)entry*BS2, r, sum);
-			if(SCALE) {
-				const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
-				const double sr = __ldg(scale + (size_t)row*BS + r);
-#pragma unroll
-				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)col*BS + c);
-			}
-		}
-		// products: warp-uniform trip count, partner blocks exchanged within the group.  For a
-		// diagonal entry of a structurally symmetric matrix the pairs are (p, p), (p+1, p+1), ...:
-		// both partners stream.
-		const int ps = active ? meta.y : 0, pe = active ? meta.z : 0;
-		const int nk = __reduce_max_sync(0xffffffffu, pe - ps);
-		for(int k = 0; k < nk; k++) {
-			const bool has = ps + k < pe;
-			int2 pr = make_int2(0, 0);
-			if(has) pr = __ldg(pairs + ps + k);
-			double lr[BS], ur[BS];
-#pragma unroll
-			for(int m = 0; m < BS; m++) { lr[m] = 0; ur[m] = 0; }
-			if(has) {
-				BlkIO<BS>::template load_row<true>(lval + (size_t)pr.x*BS2, r, lr);
-				BlkIO<BS>::template load_row<true>(ut + (size_t)pr.y*BS2, r, ur);
-			}
-			group_mul_sub<BS>(sum, lr, ur, g*BS);
-		}
-		if(active) {
-			double *op = isdiag ? udiag + (size_t)(~meta.w)*BS2 : ut + (size_t)meta.w*BS2;
-			if(changed && row_differs<BS>(op, r, sum)) *changed = 1;
-			BlkIO<BS>::store_row(op, r, sum);
-		}
-		// a diagonal entry refreshes the compact inverse by the cooperative Gauss-Jordan of
-		// blockops.cuh::group_inverse (row m of the new block lives in lane m)
-		if(__any_sync(0xffffffffu, isdiag)) {
-			double x[BS];
-			int prow;
-			group_inverse<BS>(sum, x, g*BS, r, prow);
-			if(isdiag) BlkIO<BS>::store_row(dinv + (size_t)(~meta.w)*BS2, prow, x);
-		}
+		upper_item<BS,SCALE>(meta, g, r, browind, bcolind, avals, pairs, scale, dinv, lval, ut, udiag, changed);
 		meta = metan; metan = metann;
 		t += stride;
 	}
+}
+
+// ------------------------------------------------------------------ exact block ILU(0), one launch
+
+__device__ __forceinline__ int ld_poll_flag(const int *p)
+{
+	int v;
+	asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+/// Exact ("sequential") point-block ILU(0) in ONE launch instead of iterating sweeps to the fixed
+/// point (up to one sweep per dependency level: 2047 on C2).  A group of BS lanes per block row;
+/// rows are taken from a level-sorted list in which every level is padded to whole warps (slot
+/// value -1), so the rows of a warp are mutually independent; CTAs take their position from a
+/// ticket counter, so every row a warp can wait for belongs to a CTA that has already started.  A
+/// warp waits until all rows named by its rows' lower parts have raised their flags, then every
+/// group walks its own row in storage order - lower entries, diagonal, upper entries: the
+/// reference's sequential pass (tests/solverops/async_ilu_convergence.cpp:462-490,
+/// src/solverfactory.cpp:93-107) - with the very per-entry arithmetic of the sweep launches
+/// (lower_item / upper_item), hence the same values as their fixed point.  The spin is bounded
+/// (error flag), as in the one-launch substitutions of apply.cu.
+template <int BS, bool SCALE>
+__global__ void __launch_bounds__(256)
+block_ilu0_exact_kernel(const int nslots, const int *__restrict__ slots, const int *__restrict__ lptr,
+                        const int *__restrict__ uptr, const int *__restrict__ lcol,
+                        const int4 *__restrict__ lmeta, const int4 *__restrict__ uall,
+                        const int *__restrict__ browind, const int *__restrict__ bcolind,
+                        const double *__restrict__ avals, const int2 *__restrict__ pairs,
+                        const double *__restrict__ scale, double *dinv, double *lval, double *ut,
+                        double *udiag, int *rowdone, int *__restrict__ ticket, int *__restrict__ err)
+{
+	constexpr int GPW = 32/BS;
+	__shared__ int s_cta;
+	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const int g = lane / BS, r = lane - g*BS;
+	const long long warp = (long long)s_cta*(blockDim.x >> 5) + (threadIdx.x >> 5);
+	const long long t = warp*GPW + g;
+	int row = -1;
+	if(g < GPW && t < nslots) row = __ldg(slots + t);
+	int ls = 0, le = 0, us = 0, ue = 0;
+	if(row >= 0) {
+		ls = __ldg(lptr + row); le = __ldg(lptr + row + 1);
+		us = __ldg(uptr + row) + row; ue = __ldg(uptr + row + 1) + row + 1;
+	}
+	// wait for the rows this row reads (every lane of a group polls the same flags: broadcast)
+	int kdep = ls, spins = 0;
+	while(true) {
+		while(kdep < le && ld_poll_flag(rowdone + __ldg(lcol + kdep)) != 0) kdep++;
+		if(__all_sync(0xffffffffu, kdep == le)) break;
+		__nanosleep(64);
+		if(++spins > (1 << 16) && ((spins & 1023) == 0)) {
+			if(spins > (1 << 22) || *((volatile int*)err)) { *err = 1; kdep = le; }
+		}
+	}
+	__threadfence();
+	const int nl = __reduce_max_sync(0xffffffffu, le - ls);
+	const int4 lnone = make_int4(-1, -1, 0, 0), unone = make_int4(-1, 0, 0, 0);
+	for(int e = 0; e < nl; e++) {
+		const int4 meta = (ls + e < le) ? __ldg(lmeta + ls + e) : lnone;
+		lower_item<BS,SCALE,true>(meta, ls + e, g, r, browind, avals, pairs, scale, dinv, lval, ut, nullptr);
+	}
+	const int nu = __reduce_max_sync(0xffffffffu, ue - us);
+	for(int e = 0; e < nu; e++) {
+		const int4 meta = (us + e < ue) ? __ldg(uall + us + e) : unone;
+		upper_item<BS,SCALE>(meta, g, r, browind, bcolind, avals, pairs, scale, dinv, lval, ut, udiag, nullptr);
+	}
+	__threadfence();
+	__syncwarp();
+	if(row >= 0 && r == 0) *((volatile int*)(rowdone + row)) = 1;
+}
+
+/// slots[base[l] + (i - level_ptr[l])] = level_rows[i] for row position i of level l
+__global__ void __launch_bounds__(256)
+exact_slots_kernel(const int n, const int nlevels, const int *__restrict__ level_ptr,
+                   const int *__restrict__ slot_base, const int *__restrict__ level_rows,
+                   int *__restrict__ slots)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int lo = 0, hi = nlevels - 1;                 // level of position i: last l with level_ptr[l] <= i
+	while(lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if(level_ptr[mid] <= i) lo = mid; else hi = mid - 1;
+	}
+	slots[slot_base[lo] + (i - level_ptr[lo])] = level_rows[i];
 }
 
 
@@ -680,6 +795,50 @@ void launch_ilu0_sweep(const Mat& A, const IluPattern& pl, const double *scale, 
 	if(A.bs == 4) { launch_block_sweep<4>(A, pl, scale, F, dinv, d_changed, all_upper, st); return; }
 	if(A.bs == 5) { launch_block_sweep<5>(A, pl, scale, F, dinv, d_changed, all_upper, st); return; }
 	throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+}
+
+int block_exact_slots(const Mat& A, const Levels& lv, DevBuf<int>& slots, cudaStream_t st)
+{
+	// every level padded to whole warps of groups, so that the rows of a warp never depend on one
+	// another (host prefix over the level sizes; the levels are a few thousand at most)
+	const int GPW = 32/A.bs;
+	std::vector<int> base(lv.nlevels + 1, 0);
+	for(int l = 0; l < lv.nlevels; l++) {
+		const int nl = lv.level_ptr[l+1] - lv.level_ptr[l];
+		base[l+1] = base[l] + (nl + GPW - 1)/GPW*GPW;
+	}
+	const int nslots = base[lv.nlevels];
+	slots.alloc(std::max(nslots, 1));
+	B200_CUDA(cudaMemsetAsync(slots, 0xff, (size_t)std::max(nslots, 1)*sizeof(int), st));
+	DevBuf<int> d_base;
+	d_base.alloc(lv.nlevels + 1);
+	B200_CUDA(cudaMemcpyAsync(d_base, base.data(), (lv.nlevels + 1)*sizeof(int), cudaMemcpyHostToDevice, st));
+	exact_slots_kernel<<<div_up(A.nbrows, 256), 256, 0, st>>>(A.nbrows, lv.nlevels, lv.d_level_ptr, d_base,
+	                                                       lv.level_rows, slots);
+	B200_LAUNCHED();
+	B200_CUDA(cudaStreamSynchronize(st));             // `base` and d_base go out of scope
+	return nslots;
+}
+
+void launch_ilu0_exact(const Mat& A, const IluPattern& pl, const int *slots, int nslots,
+                       const double *scale, ScalarFactor& F, double *dinv, int *rowdone, int *flags,
+                       cudaStream_t st)
+{
+	if(A.nbrows == 0) return;
+	ProfScope ps(KC_FACTOR_LOWER, st);
+	B200_CUDA(cudaMemsetAsync(rowdone, 0, (size_t)A.nbrows*sizeof(int), st));
+	B200_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));                // ticket
+	const int GPW = 32/A.bs;
+	const int grid = div_up((long long)nslots/GPW*32, 256);
+	double *ut = F.ut.p ? F.ut.p : F.uval.p;
+#define B200_EXACT(BSV, SC) block_ilu0_exact_kernel<BSV,SC><<<grid,256,0,st>>>(nslots, slots, pl.lptr, pl.uptr, \
+		pl.lcol, pl.slmeta, pl.suall, A.browind, A.bcolind, A.vals, pl.spairs, scale, dinv, F.lval.p, ut,      \
+		F.udiag.p, rowdone, flags, flags + 1)
+	if(A.bs == 4) { if(scale) B200_EXACT(4, true); else B200_EXACT(4, false); }
+	else if(A.bs == 5) { if(scale) B200_EXACT(5, true); else B200_EXACT(5, false); }
+	else throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+#undef B200_EXACT
+	B200_LAUNCHED();
 }
 
 void launch_sync_upper(const Mat& A, const IluPattern& pl, ScalarFactor& F, bool all, cudaStream_t st)

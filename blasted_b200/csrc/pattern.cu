@@ -354,6 +354,40 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.built = true;
 }
 
+// ------------------------------------------------------------------ pattern statistics
+
+__global__ void __launch_bounds__(256)
+lower_products_kernel(const long long n, const int4 *__restrict__ lmeta, unsigned long long *__restrict__ total)
+{
+	unsigned long long s = 0;
+	for(long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n;
+	    i += (long long)gridDim.x*blockDim.x) {
+		const int4 m = lmeta[i];
+		s += (unsigned long long)(m.w - m.z);
+	}
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+	if((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
+/// {lower entries, upper entries incl. diagonals, upper work entries, products of lower entries,
+/// products of upper entries}: what the byte formulas of the factor launches are made of
+void pattern_stats(const IluPattern& pl, long long out[5], cudaStream_t st)
+{
+	DevBuf<unsigned long long> d;
+	d.alloc(1);
+	B200_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), st));
+	if(pl.nlower > 0) {
+		lower_products_kernel<<<(int)std::min<long long>(div_up(pl.nlower, 256), 148*8), 256, 0, st>>>(pl.nlower, pl.slmeta, d);
+		B200_LAUNCHED();
+	}
+	unsigned long long h = 0;
+	B200_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	out[0] = pl.nlower; out[1] = pl.nupper; out[2] = pl.nuwork;
+	out[3] = (long long)h; out[4] = pl.npos - (long long)h;
+}
+
 // ------------------------------------------------------------------ split CSR only (scalar SGS)
 
 __global__ void __launch_bounds__(256)

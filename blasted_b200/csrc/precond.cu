@@ -132,6 +132,7 @@ void prec_compute(Prec& P, double precinfo[6])
 			if(scalar) scalar_ilu0_sweep(A, P.pl, scale, P.sf, flag, all_upper, st);
 			else launch_ilu0_sweep(A, P.pl, scale, P.sf, dinv, flag, all_upper, st);
 		};
+		bool wrote_all_upper = !const_upper_set;      // every upper entry was (re)written by the sweeps
 		if(P.threadedfactor) {
 			for(int sw = 0; sw < P.s.nbuildsweeps; sw++) sweep(sw, nullptr);
 			P.factor_sweeps_done = P.s.nbuildsweeps;
@@ -146,6 +147,20 @@ void prec_compute(Prec& P, double precinfo[6])
 			B200_CUDA(cudaStreamSynchronize(st));
 			if(failed) throw Error("exact factorisation did not complete: a dependency never arrived");
 			P.factor_sweeps_done = 1;
+		}
+		else if(P.s.nbuildsweeps > 0 && !scalar && exact_in_one_launch(P)) {
+			// exact block factorisation: one launch over level-sorted, warp-padded rows (factor.cu)
+			if(!P.rowdone.p) P.rowdone.alloc(std::max(A.nbrows, 1));
+			if(!P.exact_slots.p) P.n_exact_slots = block_exact_slots(A, P.levels, P.exact_slots, st);
+			B200_CUDA(cudaMemsetAsync(P.sync_flags, 0, 2*sizeof(int), st));
+			launch_ilu0_exact(A, P.pl, P.exact_slots, P.n_exact_slots, scale, P.sf, dinv, P.rowdone,
+			                  P.sync_flags, st);
+			int failed = 0;
+			B200_CUDA(cudaMemcpyAsync(&failed, P.sync_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+			B200_CUDA(cudaStreamSynchronize(st));
+			if(failed) throw Error("exact factorisation did not complete: a dependency never arrived");
+			P.factor_sweeps_done = 1;
+			wrote_all_upper = true;
 		}
 		else if(P.s.nbuildsweeps > 0) {
 			// exact factorisation: iterate to the bitwise fixed point
@@ -170,7 +185,7 @@ void prec_compute(Prec& P, double precinfo[6])
 		// blocks: the sweeps maintain the column-order copy of the strict upper part; the row-order
 		// copy the triangular solves read catches up here (no entries at all for star stencils)
 		if(!scalar && P.factor_sweeps_done > 0 && P.s.nbuildsweeps > 0)
-			launch_sync_upper(A, P.pl, P.sf, !const_upper_set, st);
+			launch_sync_upper(A, P.pl, P.sf, wrote_all_upper, st);
 
 		if(info && precinfo) {
 			precinfo[0] = scalar ? scalar_ilu0_residual(A, P.pl, scale, P.sf, P.scratch, st)
@@ -298,7 +313,10 @@ static bool exact_in_one_launch(Prec& P)
 	static const bool force_sweeps = getenv("B200_EXACT_SWEEPS") != nullptr;
 	static const bool force_one = getenv("B200_EXACT_ONE_LAUNCH") != nullptr;
 	if(force_sweeps) return false;
-	if(!force_one && P.A->nbrows < (1 << 20)) return false;
+	// blocks: a sweep costs the same whatever the size and the fixed point needs one per level, so
+	// the one-launch form wins as soon as there are more than a few levels
+	if(!force_one && P.A->bs == 1 && P.A->nbrows < (1 << 20)) return false;
+	if(!force_one && P.A->bs > 1 && P.levels.nlevels < 8) return false;
 	return one_launch_levels(P);
 }
 

@@ -147,41 +147,6 @@ def _slab_couplings(nx, ny, z0, z1, rank, world, diag) -> LocalPart:
                      np.concatenate(sidx) if sidx else np.zeros(0, np.int32), recv_counts)
 
 
-def poisson3d_device(dims, device="cuda", planes_per_chunk: int = 8):
-    """The 7-point Laplacian of matgen.poisson3d(dims=...) assembled ON the device with torch (the
-    512^3 operator has 9.4e8 entries: building it with numpy on the host would take longer than
-    solving with it).  Returns int32 browptr, int32 bcolind, float64 vals as CUDA tensors; same
-    entries in the same order as the host generator (tests/test_gpu_dist.py)."""
-    import torch
-    nx, ny, nz = dims
-    plane = nx*ny
-    n = plane*nz
-    if 7*n >= 2**31:
-        raise ValueError("pattern exceeds int32 indexing")
-    offs = torch.tensor([-plane, -nx, -1, 0, 1, nx, plane], dtype=torch.int64, device=device)
-    counts, cols, diagv = [], [], []
-    for z0 in range(0, nz, planes_per_chunk):
-        z1 = min(nz, z0 + planes_per_chunk)
-        idx = torch.arange(z0*plane, z1*plane, dtype=torch.int64, device=device)
-        x = idx % nx
-        y = (idx // nx) % ny
-        z = idx // plane
-        valid = torch.stack([z > 0, y > 0, x > 0, torch.ones_like(x, dtype=torch.bool),
-                             x < nx - 1, y < ny - 1, z < nz - 1], dim=1)
-        c = idx[:, None] + offs[None, :]
-        counts.append(valid.sum(dim=1, dtype=torch.int32))
-        cols.append(c[valid].to(torch.int32))
-        diagv.append((offs[None, :] == 0).expand_as(valid)[valid])
-    counts = torch.cat(counts)
-    browptr = torch.zeros(n + 1, dtype=torch.int32, device=device)
-    browptr[1:] = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
-    bcolind = torch.cat(cols)
-    del cols
-    isdiag = torch.cat(diagv)
-    vals = torch.where(isdiag, 6.0, -1.0).to(torch.float64)
-    return browptr, bcolind, vals
-
-
 def poisson3d_slab_device(n: int, rank: int, world: int, dims=None):
     """poisson3d_slab with the diagonal block assembled on the device: returns (part, diag_view)
     where part.diag is None (no host copy of the big block) and the couplings to the neighbouring
@@ -189,6 +154,7 @@ def poisson3d_slab_device(n: int, rank: int, world: int, dims=None):
     nx, ny, nz = (n, n, n) if dims is None else dims
     zoff = row_offsets(nz, world)
     z0, z1 = int(zoff[rank]), int(zoff[rank+1])
+    from .matgen_device import poisson3d_device
     browptr, bcolind, vals = poisson3d_device((nx, ny, z1 - z0))
     view = SRMatrixView.from_device(nx*ny*(z1 - z0), 1, browptr, bcolind, vals)
     del browptr, bcolind, vals

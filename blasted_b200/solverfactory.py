@@ -322,11 +322,22 @@ class Preconditioner:
                                           upperp.ctypes.data_as(C.c_void_p)))
         return posptr, lowerp[:npos.value], upperp[:npos.value]
 
+    def pattern_stats(self) -> dict:
+        """Work-list sizes {nlower, nupper, nuwork, npos_l, npos_u} without copying the lists."""
+        out = (C.c_longlong*5)()
+        check(lib.b200_prec_pattern_stats(self._h, out))
+        return dict(zip(("nlower", "nupper", "nuwork", "npos_l", "npos_u"), [int(v) for v in out]))
+
+    def nlevels(self) -> int:
+        nl = C.c_int()
+        check(lib.b200_prec_levels_size(self._h, C.byref(nl)))
+        return nl.value
+
     def levels(self):
         nl = C.c_int()
         check(lib.b200_prec_levels_size(self._h, C.byref(nl)))
         ptr = np.empty(nl.value + 1, dtype=np.int32)
-        rows = np.empty(self.view.m.nbrows, dtype=np.int32)
+        rows = np.empty(lib.b200_mat_nbrows(self.view._h), dtype=np.int32)
         check(lib.b200_prec_get_levels(self._h, ptr.ctypes.data_as(C.c_void_p),
                                        rows.ctypes.data_as(C.c_void_p)))
         return ptr, rows

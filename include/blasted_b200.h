@@ -209,6 +209,11 @@ int b200_prec_set_sweeps(b200_prec *p, int nbuildsweeps, int napplysweeps);
 /** ILUPositions (include/ilu_pattern.hpp:36-48) built on the device: sizes, then copy-out. */
 int b200_prec_positions_size(b200_prec *p, long long *npos);
 int b200_prec_get_positions(b200_prec *p, int *posptr, int *lowerp, int *upperp);
+/** Sizes of the work lists built from the position lists, without copying them out: stats =
+ *  {lower entries, upper entries incl. diagonals, upper entries that change between sweeps (have
+ *  products or are diagonal), products of lower entries, products of upper entries} - what the
+ *  algorithmic byte counts of the factor launches are made of (bench.py). */
+int b200_prec_pattern_stats(b200_prec *p, long long stats[5]);
 /** Level schedule.  CONTIGUOUS mode: `levels` (nlevels+1 entries) as computeLevels returns.
  *  DAG mode: level pointers (nlevels+1) and the row list ordered by level (nbrows). */
 int b200_prec_levels_size(b200_prec *p, int *nlevels);

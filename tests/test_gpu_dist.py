@@ -78,17 +78,32 @@ def test_distributed_spmv_and_solve():
 
 
 def test_device_poisson_generator_matches_host():
-    """dist.poisson3d_device assembles exactly the arrays of matgen.poisson3d (the 512^3 bench
-    operator is built with it), also when the planes are processed in ragged chunks."""
+    """matgen_device assembles exactly the arrays of matgen.poisson3d (the 512^3 and 27-point
+    256^3 bench operators are built with it), also when the rows are processed in ragged chunks;
+    the device block-stencil generator follows the host recipe (pattern identical, blocks
+    block-diagonally dominant)."""
     import torch
     from blasted_b200 import matgen
-    from blasted_b200.dist import poisson3d_device
-    for dims, chunk in (((7, 5, 9), 4), ((16, 12, 10), 3), ((5, 5, 1), 8)):
-        m = matgen.poisson3d(0, 7, dims=dims)
-        bp, bc, v = poisson3d_device(dims, planes_per_chunk=chunk)
+    from blasted_b200 import matgen_device as md
+    for dims, st, chunk in (((7, 5, 9), 7, 100), ((16, 12, 10), 7, 333), ((5, 5, 3), 27, 8), ((9, 7, 6), 27, 1 << 21)):
+        m = matgen.poisson3d(0, st, dims=dims)
+        bp, bc, slot, offs = md.stencil_pattern_device(dims, st == 27, rows_per_chunk=chunk)
         assert np.array_equal(bp.cpu().numpy(), m.browptr)
         assert np.array_equal(bc.cpu().numpy(), m.bcolind)
+        bp, bc, v = md.poisson3d_device(dims, st)
         assert np.array_equal(v.cpu().numpy(), m.vals)
+    for dims, bs in (((12, 9), 4), ((6, 5, 4), 5)):
+        m = matgen.block_stencil(dims, bs, 1)
+        nb, bp, bc, v = md.block_stencil_device(dims, bs, 1)
+        assert nb == m.nbrows and np.array_equal(bp.cpu().numpy(), m.browptr)
+        assert np.array_equal(bc.cpu().numpy(), m.bcolind)
+        blocks = v.cpu().numpy().reshape(-1, bs, bs).transpose(0, 2, 1)          # logical [r, c]
+        rows = np.repeat(np.arange(nb), np.diff(m.browptr))
+        off = np.abs(blocks).sum(axis=2).max(axis=1)
+        off[m.diagind] = 0
+        rowsum = np.bincount(rows, weights=off, minlength=nb)
+        d = blocks[m.diagind]
+        assert np.all(np.abs(d[:, np.arange(bs), np.arange(bs)]) > rowsum[:, None] + 0.7)
 
 
 def test_slab_device_solve_matches_host_assembled():

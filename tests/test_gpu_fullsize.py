@@ -122,3 +122,86 @@ def test_c4_27point_scaled_factor_properties():
         prectype=SOLVER_TYPES["sfilu0"], bs=1, scale=True, nbuildsweeps=1))
     q.compute()
     assert relerr(p.factor(), q.factor()) < 1e-9
+
+
+# ------------------------------------------------------------------ against the compiled reference
+#
+# oracle/_ref/libblasted_ref.so (the unmodified reference sources, built by oracle/Makefile) travels
+# to the GPU box: at BASELINE.json's full sizes the device results are compared element-wise with
+# the reference's own sequential pass, not only with this repository's exact path.
+
+from oracle import have_ref, ref, orc          # noqa: E402
+
+needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+
+
+def _uninvert_diag(m, factor):
+    """The reference inverts the diagonal blocks in place after the sweeps
+    (async_blockilu_factor.cpp:144-146); its residual function wants them un-inverted."""
+    bs2 = m.bs*m.bs
+    f = factor.copy().reshape(-1, bs2)
+    d = f[m.diagind].reshape(-1, m.bs, m.bs)
+    f[m.diagind] = np.linalg.inv(d).reshape(-1, bs2)
+    return f.reshape(-1)
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_fullsize_factor_and_residual_match_compiled_reference(cfg):
+    """Converged asynchronous block-ILU(0) on the full C2 / C3 matrices against the reference's
+    sequential pass (tests/solverops/async_ilu_convergence.cpp:462-490): factor within 1e-12
+    element-wise, nonlinear residual ||(A-LU)_S||/||A|| within 1e-10 of the reference's
+    (:571-575; the north_star criterion for the asynchronous paths)."""
+    if cfg == "C2":
+        m = matgen.block_stencil((1024, 1024), 4, SEED + 2)
+        sweeps = 14
+    else:
+        m = matgen.block_stencil((128, 128, 128), 5, SEED + 3)
+        sweeps = 14
+    R = ref()
+    rp = R.prec(m, "seqilu0", nbuildsweeps=1, napplysweeps=1)
+    rp.compute()
+    want = rp.factor()                               # matrix order, diagonal blocks inverted
+    rp.close()
+    view = bb.SRMatrixView(m)
+    p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["ilu0"], bs=m.bs, nbuildsweeps=sweeps, napplysweeps=1))
+    p.compute()
+    got = p.factor()
+    assert relerr(got, want) < 1e-12
+    # nonlinear residual, normalised by the entry-wise 1-norm of A
+    anorm = np.abs(m.vals).sum()
+    res_dev = p.ilu_residual()
+    if m.bs == 4:
+        res_ref = R.ilu_nonlinear_res(m, None, _uninvert_diag(m, want))
+    else:
+        # the reference instantiates its residual only for bs 1 and 4 (async_blockilu_factor.cpp:299-310):
+        # the restatement (pinned against it on bs 4) evaluates the reference factor for bs 5
+        O = orc()
+        res_ref = O.ilu0_nonlinear_res(m, O.ilu_positions(m), None, _uninvert_diag(m, want))
+    assert abs(res_dev - res_ref)/anorm < 1e-10, (res_dev, res_ref, anorm)
+    assert res_dev/anorm < 1e-12
+    # and the exact ("sequential") device factorisation is the same factor
+    q = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["sfilu0"], bs=m.bs, nbuildsweeps=1))
+    q.compute()
+    assert relerr(q.factor(), want) < 1e-12
+
+
+@needs_ref
+def test_c2_apply_matches_compiled_reference():
+    """Full C2: converged asynchronous triangular sweeps against the reference's sequential
+    substitution on its own factor (solverops_ilu0.cpp:56-148), 1e-10 relative."""
+    m = matgen.block_stencil((1024, 1024), 4, SEED + 2)
+    R = ref()
+    rp = R.prec(m, "seqilu0", nbuildsweeps=1, napplysweeps=1)
+    rp.compute()
+    r = np.random.default_rng(SEED + 7).standard_normal(m.dim)
+    want = rp.apply(r)
+    rp.close()
+    view = bb.SRMatrixView(m)
+    for ptype, kw in (("ilu0", dict(nbuildsweeps=14, napplysweeps=40)), ("seqilu0", dict(nbuildsweeps=1))):
+        p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+            prectype=SOLVER_TYPES[ptype], bs=4, **kw))
+        p.compute()
+        assert relerr(p.apply(r), want) < (1e-10 if ptype == "ilu0" else 1e-12), ptype

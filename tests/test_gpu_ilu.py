@@ -120,14 +120,29 @@ def test_async_apply_converges_to_exact_substitution(key, ainit):
 
 
 @pytest.mark.parametrize("key", ["2dcyl1_bsr4", "msc00726_csr"])
-def test_apply_with_few_sweeps_matches_jacobi_bracket(key):
-    """One async L sweep from y=0 lies between the synchronous (Jacobi) and the sequential result;
-    in both cases row 0 of y (no dependencies) is exact."""
+def test_apply_sweeps_bracketed_by_level_count(key):
+    """The bracket of the asynchronous triangular sweeps: one sweep is what a synchronous
+    (Jacobi-type) sweep gives at worst, and `nlevels` sweeps are the exact substitution whatever
+    the interleaving - a row is final once the rows it reads are, so every sweep finalises at least
+    one more dependency level (the iteration matrix is nilpotent of index nlevels).  Checked:
+    k = nlevels sweeps reproduce the reference's sequential substitution to rounding, fewer sweeps
+    give finite values, and on the diagonally dominant case the error shrinks with the sweeps."""
     g, m = golden_outputs(), case(key)
+    r, want = g[key + "_r"], g[key + "_ilu_apply"]
+    lv = make(m, "async_level_ilu0", nbuildsweeps=1)
+    lv.compute()
+    nlevels = len(lv.levels()[0]) - 1
     p = make(m, "sfilu0", napplysweeps=1)
     p.compute()
-    z = p.apply(g[key + "_r"])
-    assert np.all(np.isfinite(z))
+    errs = {}
+    for k in (1, 2, 4, nlevels):
+        p.set_sweeps(1, k)
+        z = p.apply(r)
+        assert np.all(np.isfinite(z))
+        errs[k] = relerr(z, want)
+    assert errs[nlevels] < 1e-12, errs
+    if key.startswith("2dcyl1"):
+        assert errs[4] < errs[1], errs
 
 
 def test_level_scheduled_ilu_apply_both_modes():
@@ -137,7 +152,12 @@ def test_level_scheduled_ilu_apply_both_modes():
         for mode in (0, 1):
             p = make(m, "async_level_ilu0", nbuildsweeps=150, level_mode=mode)
             p.compute()
-            assert relerr(p.apply(g[key + "_r"]), g[key + "_ilu_apply"]) < 1e-11
+            assert relerr(p.apply(g[key + "_r"]), g[key + "_ilu_apply"]) < 1e-12
+    # the same substitution on the exact ("sequential") factor
+    for key in CASES:
+        p = make(case(key), "seqilu0")
+        p.compute()
+        assert relerr(p.apply(g[key + "_r"]), g[key + "_ilu_apply"]) < 1e-12
 
 
 def test_reference_error_behaviour():

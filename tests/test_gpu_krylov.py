@@ -10,6 +10,11 @@ from util import case, golden_outputs, golden_matrices, relerr
 
 pytestmark = pytest.mark.gpu
 
+# iteration counts of the unmodified reference over OpenMP thread counts 1..16 where they vary
+# through the reduction order of the dot products alone (measured on the GPU box's host by
+# tools/its_probe.py with oracle/_ref; min, max)
+REF_THREAD_SPREAD = {("msc00726_csr", "jacobi", "bicgstab"): (71, 76)}
+
 # device type whose result equals the reference's sequential preconditioner
 EXACT = {"seqilu0": "seqilu0", "sgs": "level_sgs", "jacobi": "jacobi"}
 
@@ -37,10 +42,19 @@ def test_iteration_counts_match_sequential_reference(key, prec, solver):
     x, info = solve(m, EXACT[prec], solver, b)
     assert info.converged or info.resnorm/info.bnorm < 1e-10
     # within 5 % (+1 iteration of slack for tiny counts): rounding differs, the algorithm does not.
-    # msc00726 (cond ~4e5) with a weak preconditioner makes BiCGSTAB's count sensitive to rounding
-    # of the dot products themselves (the reference's own OpenMP reductions reorder them too).
-    tol = 0.15 if (key.startswith("msc") and prec != "seqilu0") else 0.05
-    assert abs(info.iters - want_its) <= max(1, int(np.ceil(tol*want_its))), (info.iters, want_its)
+    # One case needs the reference's OWN spread as the yardstick: msc00726 (cond ~4e5) with the
+    # weakest preconditioner makes BiCGSTAB's count depend on the rounding of the dot products, and
+    # the reference's OpenMP reductions reorder them with the thread count - the unmodified
+    # reference needs 71, 76, 72, 76, 76, 76, 74, 76 iterations with 1, 2, 3, 4, 6, 8, 12, 16 threads
+    # (Jacobi itself does not depend on threads; tools/its_probe.py, profiles/its_probe_r02.log).
+    # The device count has to lie within 5 % of that range; every other case within 5 % of the
+    # sequential count.
+    lo = hi = want_its
+    if (key, prec, solver) == ("msc00726_csr", "jacobi", "bicgstab"):
+        lo, hi = REF_THREAD_SPREAD[(key, prec, solver)]
+        assert lo <= want_its <= hi
+    slack = lambda w: max(1, int(np.ceil(0.05*w)))
+    assert lo - slack(lo) <= info.iters <= hi + slack(hi), (info.iters, want_its, lo, hi)
     # and the solution solves the system
     res = np.linalg.norm(b - orc().spmv(m, x))/np.linalg.norm(b)
     assert res < 5e-10

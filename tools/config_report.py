@@ -40,52 +40,70 @@ def row(name, ms, nbytes):
     print(f"| {name} | {ms:.3f} | {nbytes/1e9:.3f} | {gbs:.0f} | {gbs/PEAK:.2f} |")
 
 
-def pattern_counts(m, posptr):
-    rows = np.repeat(np.arange(m.nbrows), np.diff(m.browptr))
-    cnt = np.diff(posptr)
-    low = m.bcolind < rows
-    dg = m.bcolind == rows
-    return dict(nl=int(low.sum()), nu=int((~low).sum()), nuw=int(((~low) & ((cnt > 0) | dg)).sum()),
-                pl=int(cnt[low].sum()), pu=int(cnt[~low].sum()))
+def kernel_bytes(bs, N, nnz, c, scale=False):
+    """Algorithmic bytes per launch of every kernel class; c = pattern_stats()."""
+    b, b2 = bs, bs*bs
+    out = {"spmv": (8*b2+4)*nnz + 4*(N+1) + 16*b*N}
+    if b == 1:
+        out["factor_lower"] = 32*c["nlower"] + 8*N + 24*c["npos_l"] + (8*c["nlower"] if scale else 0)
+        out["factor_upper"] = 32*c["nuwork"] + 24*c["npos_u"]
+        out["tri_lower"] = 12*c["nlower"] + 4*N + 24*N
+        out["tri_upper"] = 12*(c["nupper"] - N) + 4*N + 32*N
+    else:
+        out["factor_lower"] = c["nlower"]*(16*b2+16) + 8*b2*N + c["npos_l"]*(16*b2+8)
+        out["factor_upper"] = c["nuwork"]*(16*b2+16) + c["npos_u"]*(16*b2+8) + 8*b2*N
+        out["tri_lower"] = c["nlower"]*(8*b2+4) + 8*N + 24*b*N
+        out["tri_upper"] = (c["nupper"]-N)*(8*b2+4) + 8*N + 24*b*N + 8*b2*N
+    return out
 
 
-def report(title, m, nb=3, na=3, scale=False, sgs=False, levels=False, solve=None):
-    b, N, nnz = m.bs, m.nbrows, m.nnzb
+def measure(view, bs, N, nnz, nb=3, na=3, scale=False, steps=5, peak=None):
+    """CUDA-event time of every kernel class on a resident matrix -> {kernel: {ms, bytes, gbs, frac}},
+    plus the preconditioner (for further use), first-compute time and the pattern statistics."""
+    peak = peak or PEAK
+    x = torch.randn(N*bs, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["ilu0"], bs=bs, nbuildsweeps=nb, napplysweeps=na, scale=scale)
+    p = bb.SRFactory().create_preconditioner(view, s)
+    torch.cuda.synchronize(); t0 = time.time(); p.compute(); torch.cuda.synchronize(); setup = time.time() - t0
+    c = p.pattern_stats()
+    kb = kernel_bytes(bs, N, nnz, c, scale)
+    p.compute(); p.apply(x, y)
+    sf.profile_reset(); sf.profile_enable(True)
+    for _ in range(steps):
+        p.compute(); p.apply(x, y)
+    prof = sf.profile_get(); sf.profile_enable(False)
+    ms = {k: v[0]/max(v[1], 1) for k, v in prof.items()}
+    ms["spmv"] = timeit(lambda: view.apply(x, y))
+    out = {}
+    for k, nbytes in kb.items():
+        if ms.get(k, 0) > 0:
+            gbs = nbytes/ms[k]/1e6
+            out[k] = {"ms": ms[k], "bytes": int(nbytes), "gbs": gbs, "frac": gbs/peak}
+    return out, p, setup, c, (x, y)
+
+
+def report(title, m, nb=3, na=3, scale=False, sgs=False, levels=False, solve=None, view=None, dims=None):
+    """m: host SRMatrix, or None with view = device-assembled SRMatrixView and dims = (bs, N, nnz)."""
+    if m is not None:
+        view = bb.SRMatrixView(m)
+        b, N, nnz = m.bs, m.nbrows, m.nnzb
+    else:
+        b, N, nnz = dims
     b2 = b*b
     print(f"\n### {title}\n\nN = {N} (block) rows, nnzb = {nnz}, bs = {b}, scale = {scale}; peak = {PEAK:.0f} GB/s (measured)\n")
     print("| kernel | ms | algorithmic GB | GB/s | frac of measured peak |\n|---|---|---|---|---|")
-    view = bb.SRMatrixView(m)
-    x = torch.randn(m.dim, dtype=torch.float64, device="cuda")
-    y = torch.empty_like(x)
-    row("SpMV y=Ax", timeit(lambda: view.apply(x, y)), (8*b2+4)*nnz + 4*(N+1) + 16*b*N)
-    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["ilu0"], bs=b, nbuildsweeps=nb, napplysweeps=na, scale=scale)
-    p = bb.SRFactory().create_preconditioner(view, s)
-    t0 = time.time(); p.compute(); torch.cuda.synchronize(); setup = time.time() - t0
-    posptr, lowerp, _ = p.ilu_positions()
-    c = pattern_counts(m, posptr)
-    sf.profile_reset(); sf.profile_enable(True)
-    for _ in range(5):
-        p.compute(); p.apply(x, y)
-    prof = sf.profile_get(); sf.profile_enable(False)
-    avg = {k: v[0]/max(v[1], 1) for k, v in prof.items()}
-    if b == 1:
-        fl = 32*c["nl"] + 8*N + 24*c["pl"] + (8*c["nl"] if scale else 0)
-        fu = 32*c["nuw"] + 24*c["pu"]
-        tl = 12*c["nl"] + 4*N + 24*N
-        tu = 12*(c["nu"] - N) + 4*N + 32*N
-    else:
-        fl = c["nl"]*(16*b2+16) + 8*b2*N + c["pl"]*(16*b2+8)
-        fu = c["nuw"]*(16*b2+16) + c["pu"]*(16*b2+8) + 8*b2*N
-        tl = c["nl"]*(8*b2+4) + 8*N + 24*b*N
-        tu = (c["nu"]-N)*(8*b2+4) + 8*N + 24*b*N + 8*b2*N
-    row("ILU(0) factor sweep, lower launch", avg["factor_lower"], fl)
-    row("ILU(0) factor sweep, upper launch", avg["factor_upper"], fu)
-    row("async L sweep (apply)", avg["tri_lower"], tl)
-    row("async U sweep (apply)", avg["tri_upper"], tu)
+    kern, p, setup, c, (x, y) = measure(view, b, N, nnz, nb, na, scale)
+    names = {"spmv": "SpMV y=Ax", "factor_lower": "ILU(0) factor sweep, lower launch",
+             "factor_upper": "ILU(0) factor sweep, upper launch", "tri_lower": "async L sweep (apply)",
+             "tri_upper": "async U sweep (apply)"}
+    for k, nm in names.items():
+        if k in kern:
+            row(nm, kern[k]["ms"], kern[k]["bytes"])
     tot_c = timeit(lambda: p.compute(), reps=5)
     tot_a = timeit(lambda: p.apply(x, y), reps=5)
     print(f"\ncompute() with {nb} sweeps: {tot_c:.3f} ms; apply() with {na} sweep pairs: {tot_a:.3f} ms; "
-          f"first compute incl. device pattern build: {setup*1e3:.0f} ms; npos = {len(lowerp)}")
+          f"first compute incl. device pattern build: {setup*1e3:.0f} ms; npos = {c['npos_l'] + c['npos_u']}")
     res = []
     for k in (1, 2, 3, 5, 10, 20):
         p.set_sweeps(k, na); info = None
@@ -98,25 +116,47 @@ def report(title, m, nb=3, na=3, scale=False, sgs=False, levels=False, solve=Non
         t = timeit(lambda: ps.apply(x, y), reps=5)
         print(f"\nasync SGS apply ({na} fwd + {na} bwd sweeps): {t:.3f} ms "
               f"({na*((8*b2+4)*nnz + 12*N + 48*b*N + 8*b2*N)/t/1e6:.0f} GB/s)")
+        if isinstance(sgs, tuple):
+            # SGS-preconditioned FGMRES time to solve (BASELINE config 3 as named)
+            ps.set_sweeps(1, sgs[0])
+            bvec = view.apply(torch.ones(N*b, dtype=torch.float64, device="cuda"))
+            sol = bb.FGMRES(view, ps, 30); sol.setParams(1e-8, 2000)
+            for rep in range(2):
+                xs = torch.zeros_like(bvec)
+                info = sol.solve(bvec, xs)
+            print(f"\nFGMRES(30) + async block SGS ({sgs[0]} fwd + {sgs[0]} bwd sweeps): {info.iters} iterations, "
+                  f"{info.walltime*1e3:.1f} ms to rel. residual {info.resnorm/info.bnorm:.1e}, max error {float((xs-1).abs().max()):.1e}")
     if levels:
         for mode, nm in ((0, "DAG wavefronts"),):
             pl = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
                 prectype=SOLVER_TYPES["async_level_ilu0"], bs=b, nbuildsweeps=nb, scale=scale, level_mode=mode))
-            t0 = time.time(); pl.compute(); torch.cuda.synchronize(); ts = time.time() - t0
-            ptr, _ = pl.levels()
+            torch.cuda.synchronize(); t0 = time.time(); pl.compute(); torch.cuda.synchronize(); ts = time.time() - t0
+            nlev = pl.nlevels()
             t = timeit(lambda: pl.apply(x, y), reps=3, warm=1)
-            print(f"\nlevel-scheduled exact ILU(0) apply ({nm}): {len(ptr)-1} levels, {t:.3f} ms per apply "
-                  f"(vs {tot_a/na:.3f} ms per async sweep pair); level build {ts*1e3:.0f} ms")
+            print(f"\nlevel-scheduled exact ILU(0) apply ({nm}): {nlev} levels, {t:.3f} ms per apply "
+                  f"(vs {tot_a/na:.3f} ms per async sweep pair); first compute incl. level build {ts*1e3:.0f} ms")
     if solve:
         p.set_sweeps(*solve)
         p.compute()
-        bvec = view.apply(torch.ones(m.dim, dtype=torch.float64, device="cuda"))
+        bvec = view.apply(torch.ones(N*b, dtype=torch.float64, device="cuda"))
         for name, cls in (("FGMRES(30)", lambda: bb.FGMRES(view, p, 30)), ("GCR(30)", lambda: bb.GCR(view, p, 30))):
             sol = cls(); sol.setParams(1e-8, 2000)
             xs = torch.zeros_like(bvec)
             info = sol.solve(bvec, xs)
             print(f"\n{name} + async ILU(0) sweeps {solve}: {info.iters} iterations, {info.walltime*1e3:.1f} ms, "
                   f"rel. residual {info.resnorm/info.bnorm:.1e}, max error {float((xs-1).abs().max()):.1e}")
+
+
+def device_view(kind, dims, bs=1, seed=0):
+    """Device-assembled operators of the full BASELINE sizes -> (view, (bs, N, nnz))."""
+    from blasted_b200 import matgen_device as md
+    if kind == "block":
+        nb, bp, bc, v = md.block_stencil_device(dims, bs, seed)
+    else:
+        bp, bc, v = md.poisson3d_device(dims, kind)
+        nb = bp.numel() - 1
+    view = bb.SRMatrixView.from_device(nb, bs, bp, bc, v)
+    return view, (bs, nb, int(bc.numel()))
 
 
 def frontend_report():
@@ -180,12 +220,18 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "frontend"]
     print(f"# Per-kernel throughput on the BASELINE configs ({torch.cuda.get_device_name(0)})")
     if "c1" in which:
-        report("C1 - 7-point Poisson 256^3, CSR", matgen.poisson3d(256), solve=(5, 5), levels=True, sgs=True)
+        v, d = device_view(7, (256, 256, 256))
+        report("C1 - 7-point Poisson 256^3, CSR", None, solve=(5, 5), levels=True, sgs=True, view=v, dims=d)
+        del v
     if "c2" in which:
-        report("C2 - BSR bs=4, 1024x1024 cells (headline)", matgen.block_stencil((1024, 1024), 4, 20261020), sgs=True, solve=(3, 3))
+        report("C2 - BSR bs=4, 1024x1024 cells (headline)", matgen.block_stencil((1024, 1024), 4, 20261020), sgs=(3,), solve=(3, 3))
     if "c3" in which:
-        report("C3 - BSR bs=5, 128^3 cells", matgen.block_stencil((128, 128, 128), 5, 20261021), sgs=True, solve=(3, 3))
+        v, d = device_view("block", (128, 128, 128), 5, 20261021)
+        report("C3 - BSR bs=5, 128^3 cells", None, sgs=(3,), solve=(3, 3), view=v, dims=d)
+        del v
     if "c4" in which:
-        report("C4 - 27-point Poisson 192^3, CSR (scaled)", matgen.poisson3d(192, 27), scale=True, levels=True, sgs=True, solve=(10, 20))
+        v, d = device_view(27, (256, 256, 256))
+        report("C4 - 27-point Poisson 256^3, CSR (scaled)", None, scale=True, levels=True, sgs=True, solve=(10, 20), view=v, dims=d)
+        del v
     if "frontend" in which:
         frontend_report()
