@@ -336,9 +336,29 @@ def run_b200(args):
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_val = world*by["step"]*esteps/float(t_e2e.item())/1e9
+    e2e_s = float(t_e2e.item())/esteps
+    e2e_val = world*by["step"]/e2e_s/1e9
     checksum = float(np.abs(z_np).sum())
     assert np.isfinite(checksum)
+    # what the PCIe link alone allows: the same bytes as plain pinned copies (all ranks at once,
+    # as in the step), measured here
+    dev_buf = torch.empty(m.vals.size, dtype=torch.float64, device="cuda")
+    zsrc = torch.empty(m.dim, dtype=torch.float64, device="cuda")
+    link = {}
+    for name, fn, nbytes in (("h2d", lambda: dev_buf.copy_(vals_pin, non_blocking=True), m.vals.nbytes),
+                             ("d2h", lambda: z_pin.copy_(zsrc, non_blocking=True), z_np.nbytes)):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tt = torch.tensor([(time.perf_counter() - t0)/3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        link[name] = nbytes/float(tt.item())/1e9
+    del dev_buf, zsrc
+    link_bound_s = (m.vals.nbytes + r_np.nbytes)/(link["h2d"]*1e9) + z_np.nbytes/(link["d2h"]*1e9)
 
     # ---- second half of the metric: FGMRES (restarted GCR == FGMRES in exact arithmetic) time to
     # solve, 7-point Poisson n^3 row-partitioned into z-slabs over the ranks (STRONG scaling),
@@ -413,7 +433,12 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "GB/s",
                     "h2d_bytes_per_step": int(m.vals.nbytes + r_np.nbytes),
-                    "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps},
+                    "d2h_bytes_per_step": int(z_np.nbytes), "steps": esteps,
+                    "ms_per_step": e2e_s*1e3, "h2d_gbs_measured": link["h2d"], "d2h_gbs_measured": link["d2h"],
+                    "link_bound_ms_per_step": link_bound_s*1e3,
+                    "frac_of_link_bound": link_bound_s/e2e_s,
+                    "note": "host-pointer C ABI: the 704 MB of new Jacobian values cross PCIe every step; "
+                            "link_bound = the same bytes as plain pinned copies, device work excluded"},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "configs": configs,

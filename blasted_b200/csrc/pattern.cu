@@ -558,6 +558,46 @@ dag_relax_kernel(const int nbrows, const int *__restrict__ browptr, const int *_
 	}
 }
 
+/// DAG levels in ONE forward pass: level[i] = 1 + max_{j<i, a_ij != 0} level[j], level = -1 until
+/// known.  A thread per row in natural order; a row reads only lower-numbered rows, CTAs take
+/// their rows from a ticket counter, so everything a row waits for belongs to a CTA that has
+/// started.  Every pass of the loop each unfinished lane looks at its next unknown dependency
+/// once (polled at L2) - lanes of one warp may depend on each other (row i on row i-1), so nobody
+/// spins alone.  Replaces relax-until-nothing-changes (8 launches per host round trip, #levels/8
+/// round trips: 156 ms on the 7-point 256^3 matrix).
+__global__ void __launch_bounds__(256)
+dag_levels_syncfree_kernel(const int nbrows, const int *__restrict__ browptr,
+                           const int *__restrict__ bcolind, const int *__restrict__ diagind,
+                           int *level, int *__restrict__ ticket, int *__restrict__ err)
+{
+	__shared__ int s_cta;
+	if(threadIdx.x == 0) s_cta = atomicAdd(ticket, 1);
+	__syncthreads();
+	const int row = s_cta*blockDim.x + threadIdx.x;
+	bool done = row >= nbrows;
+	int jj = 0, je = 0, lv = 0;
+	if(!done) { jj = __ldg(browptr + row); je = __ldg(diagind + row); }
+	int spins = 0;
+	while(true) {
+		if(!done) {
+			// consume every dependency that is already known, stop at the first unknown one
+			while(jj < je) {
+				int l;
+				asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(l) : "l"(level + __ldg(bcolind + jj)) : "memory");
+				if(l < 0) break;
+				lv = max(lv, l + 1);
+				jj++;
+			}
+			if(jj == je) {
+				*((volatile int*)(level + row)) = lv;
+				done = true;
+			}
+		}
+		if(__all_sync(0xffffffffu, done)) break;
+		if(++spins > (1 << 22)) { *err = 1; break; }
+	}
+}
+
 __global__ void iota_kernel(int n, int *out)
 {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -628,19 +668,32 @@ void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st)
 	}
 	DevBuf<int> level, changed, rows_in, level_sorted;
 	level.alloc(n);
-	changed.alloc(1);
-	B200_CUDA(cudaMemsetAsync(level, 0, n*sizeof(int), st));
+	changed.alloc(2);
 	const int grid = div_up(n, 256);
-	int h_changed = 1, rounds = 0;
-	while(h_changed) {
-		B200_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
-		for(int rep = 0; rep < 8; rep++) {
-			dag_relax_kernel<<<grid, 256, 0, st>>>(n, A.browptr, A.bcolind, A.diagind, level, changed);
-			B200_LAUNCHED();
-		}
-		B200_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+	static const bool relax = getenv("B200_LEVELS_RELAX") != nullptr;     // A/B switch (development)
+	if(!relax) {
+		B200_CUDA(cudaMemsetAsync(level, 0xff, n*sizeof(int), st));          // -1 = not known yet
+		B200_CUDA(cudaMemsetAsync(changed, 0, 2*sizeof(int), st));           // {ticket, error}
+		dag_levels_syncfree_kernel<<<grid, 256, 0, st>>>(n, A.browptr, A.bcolind, A.diagind, level,
+		                                                 changed.p, changed.p + 1);
+		B200_LAUNCHED();
+		int h_err = 0;
+		B200_CUDA(cudaMemcpyAsync(&h_err, changed.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
 		B200_CUDA(cudaStreamSynchronize(st));
-		if(++rounds > n + 8) throw Error("DAG level relaxation did not converge");
+		if(h_err) throw Error("DAG levels: a dependency never became known");
+	} else {
+		B200_CUDA(cudaMemsetAsync(level, 0, n*sizeof(int), st));
+		int h_changed = 1, rounds = 0;
+		while(h_changed) {
+			B200_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+			for(int rep = 0; rep < 8; rep++) {
+				dag_relax_kernel<<<grid, 256, 0, st>>>(n, A.browptr, A.bcolind, A.diagind, level, changed);
+				B200_LAUNCHED();
+			}
+			B200_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+			B200_CUDA(cudaStreamSynchronize(st));
+			if(++rounds > n + 8) throw Error("DAG level relaxation did not converge");
+		}
 	}
 	rows_in.alloc(n);
 	level_sorted.alloc(n);

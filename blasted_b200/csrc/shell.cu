@@ -332,6 +332,14 @@ int b200_shell_offers_relaxation(const b200_shell_node *node)
 	return node->prectype != B200_ILU0 && node->prectype != B200_CSC_BGS && node->prectype != B200_NO_PREC;
 }
 
+int b200_shell_type_offers_relaxation(const char *pc_type)
+{
+	if(!pc_type) return 1;
+	int t;
+	try { t = type_from_string(pc_type); } catch(...) { return 1; }       // unknown: fails at the first set-up
+	return t != B200_ILU0 && t != B200_CSC_BGS && t != B200_NO_PREC;
+}
+
 int b200_shell_info_count(const b200_shell_node *node)
 {
 	if(!node || !node->infolist) return 0;

@@ -99,6 +99,10 @@ int b200_shell_relax_device(b200_shell_node *node, const double *d_rhs, double *
 /** Whether setup_localpreconditioner_blasted registers the Richardson callback for this type
  *  (src/blasted_petsc.cpp:709-716: not for ilu0, cscbgs, none). */
 int b200_shell_offers_relaxation(const b200_shell_node *node);
+/** The same question from the -blasted_pc_type string alone, for the registration step, which runs
+ *  before the options are read into the node (the reference tests the node's still uninitialised
+ *  prectype there, :709-716).  Unknown strings answer 1; they fail at the first set-up. */
+int b200_shell_type_offers_relaxation(const char *pc_type);
 /** cleanup_blasted (src/blasted_petsc.cpp:391-401) */
 int b200_shell_cleanup(b200_shell_node *node);
 /** PrecInfo records gathered so far (PrecInfoList, include/preconditioner_diagnostics.hpp) */
