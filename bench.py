@@ -408,9 +408,14 @@ def run_b200(args):
     if dom:
         ach = kernels[dom]["achieved_gbs"]
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+        for tname in ("traffic_r02.json", "traffic_r01.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                t = json.load(open(tpath))
+                t = t.get("C2", t).get(dom)
+                traffic = t.get("dram_bytes_per_launch") if isinstance(t, dict) else t
+                break
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kby[dom]}

@@ -1,6 +1,6 @@
 """Turn the ncu reports in gpurun_out/ into the committed summaries under profiles/ (run on the CPU box)."""
 import csv, json, os, subprocess, sys, collections
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 OUT = os.path.join(ROOT, "profiles")
 os.makedirs(OUT, exist_ok=True)
@@ -12,9 +12,20 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size"]
 CLASS = {"block_ilu0_lower": "factor_lower", "block_ilu0_upper": "factor_upper",
          "tri_block_kernel<4, 0": "tri_lower", "tri_block_kernel<4, 1": "tri_upper",
-         "tri_block_kernel<5, 0": "tri_lower", "tri_block_kernel<5, 1": "tri_upper"}
+         "tri_block_pipe_kernel<4, 0": "tri_lower", "tri_block_pipe_kernel<4, 1": "tri_upper",
+         "tri_block_kernel<5, 0": "tri_lower", "tri_block_kernel<5, 1": "tri_upper",
+         "scalar_lower_kernel": "factor_lower", "scalar_upper_kernel": "factor_upper",
+         "csr_stream_kernel<2,": "tri_lower", "csr_stream_kernel<3,": "tri_upper",
+         "csr_stream_kernel<0,": "spmv", "bsr": "spmv", "csr_spmv": "spmv"}
 traffic = {}
-for w in ("c2", "c3s", "p128"):
+algbytes = {}
+for w in ("c1", "c2", "c3", "c4", "c3s", "p128"):
+    ab = os.path.join(ROOT, "gpurun_out", f"algbytes_{w}_{R}.txt")
+    if os.path.exists(ab):
+        for tok in open(ab).read().split():
+            if "=" in tok:
+                k, v = tok.split("=")
+                algbytes.setdefault(w, {})[k] = int(v)
     rawf = os.path.join(ROOT, "gpurun_out", f"raw_{w}_{R}.csv")
     if not os.path.exists(rawf):
         continue
@@ -30,7 +41,7 @@ for w in ("c2", "c3s", "p128"):
             st = sorted(((float(r[hdr.index(h)].replace(",", "") or 0), h[34:-24]) for h in stall), reverse=True)[:3]
             wr.writerow([r[hdr.index("Kernel Name")][:90]] + [r[hdr.index(c)] for c in cols[1:]] +
                         ["; ".join(f"{n}={v:.1f}" for v, n in st)])
-            if w == "c2":
+            if True:
                 name = r[hdr.index("Kernel Name")]
                 for key, cls in CLASS.items():
                     if key in name:
@@ -39,9 +50,18 @@ for w in ("c2", "c3s", "p128"):
                             return v*{"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
                         rd = gb(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
                         wrb = gb(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
-                        traffic.setdefault(cls, []).append(rd + wrb)
+                        traffic.setdefault(w.upper(), {}).setdefault(cls, []).append(rd + wrb)
+                        break
 if traffic:
-    json.dump({k: sum(v)/len(v) for k, v in traffic.items()}, open(os.path.join(OUT, f"traffic_{R}.json"), "w"), indent=1)
+    out = {}
+    for w, d in traffic.items():
+        out[w] = {}
+        for cls, v in d.items():
+            t = sum(v)/len(v)
+            a = algbytes.get(w.lower(), {}).get(cls)
+            out[w][cls] = {"dram_bytes_per_launch": t, "algorithmic_bytes_per_launch": a,
+                           "dram_over_algorithmic": (t/a if a else None)}
+    json.dump(out, open(os.path.join(OUT, f"traffic_{R}.json"), "w"), indent=1)
 # launch list: per-kernel share of the bench step
 ll = os.path.join(ROOT, "gpurun_out", f"launches_{R}.csv")
 if os.path.exists(ll):
