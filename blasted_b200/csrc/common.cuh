@@ -189,6 +189,13 @@ struct IluPattern {
 	                                     ///< column-ordered copy UT), or ~row for a diagonal
 	DevBuf<int2> spairs;                 ///< products re-indexed into the split L / U (blocks: UT) arrays
 	DevBuf<int> ut_order, utpos;         ///< blocks: UT[d] = U[ut_order[d]], utpos = inverse
+	DevBuf<int4> dmeta, dmeta_u;         ///< bs = 5 staged upper launch, per row: {A entry of the diagonal,
+	                                     ///< first L index, products, 0} and the U indices of the products
+	bool diag_runs_ok = false;           ///< lists valid: diagonals only, <= 3 products, L partners a run
+	bool diag_u_runs = false;            ///< ... and the U partners a run as well (column-ordered copy)
+	DevBuf<int4> lrow_meta, lrow_cols;   ///< bs = 5 staged lower launch, per row: {first A entry, first L
+	                                     ///< index, lower entries, 0} and the columns of the lower entries
+	bool lower_rows_ok = false;          ///< lists valid: no lower entry has products, <= 3 per row
 	DevBuf<int> lentry, uentry;          ///< split-only build (SGS): position in A of every L / U entry
 	bool built = false, split_built = false;
 };

@@ -19,45 +19,11 @@
  * HBM-bound: 12 B per stored entry + 4 B row pointer + vectors.
  */
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200 {
 
 constexpr int STREAM_CAP = 3584;       // entries staged per CTA: 28 KiB of values + 14 KiB of indices
-
-// ---- 1D bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) + mbarrier, CTA-local ----
-
-__device__ __forceinline__ unsigned smem_u32(const void *p)
-{
-	return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-	             :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
-                                         unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"WAIT_LOOP:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra WAIT_DONE;\n"
-		"bra WAIT_LOOP;\n"
-		"WAIT_DONE:\n"
-		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 template <int KIND, int LPR, int RPT, int CAP>
 __global__ void __launch_bounds__(256)

@@ -33,6 +33,7 @@
  */
 #include "common.cuh"
 #include "blockops.cuh"
+#include "tma.cuh"
 #include <cub/device/device_reduce.cuh>
 
 namespace b200 {
@@ -561,6 +562,216 @@ block_ilu0_upper_kernel(const long long nupper, const int4 *__restrict__ umeta,
 	}
 }
 
+// ------------------------------------------------------------------ bs = 5 upper launch, staged
+//
+// The bs = 5 launches are bound by the L1 data pipe: a 5-lane group reads a 200-byte block as five
+// 40-byte segments (5.6 wavefronts per load instruction) and the shuffles of the block products go
+// through the same pipe.  Where the pattern allows it (IluPattern::diag_runs_ok: the diagonals are
+// the only upper entries with products, at most three each, the L partners of row i a run
+// L[l .. l+nk) - every face-neighbour block stencil) the global half is taken off that pipe: every
+// warp stages the A block, the L run and the U partners of its six rows in shared memory with TMA
+// bulk copies (cp.async.bulk, 208 / <= 624 bytes, completing on the warp's own mbarrier; measured
+// in tools/ubench/gather5.cu: 208-byte copies at random positions arrive at 4.4 TB/s, runs of three
+// blocks at 5.9, 40-byte segment loads at 2.2) and the groups read their rows from shared memory.
+// One stage per warp and six resident CTAs of four warps: a warp's copies are covered by the other
+// warps' arithmetic (with two stages per warp the shared memory halves the resident warps and the
+// dependent chains of products and inverse are no longer covered: 0.85 against 0.69 ms on C3).
+// No CTA-wide synchronisation; same arithmetic as upper_item.
+// URUN: the U partners are an index-aligned run of the column-ordered copy (one copy instead of nk).
+
+template <bool SCALE, bool URUN>
+__global__ void __launch_bounds__(128)
+block5_upper_staged_kernel(const int nrows, const int4 *__restrict__ dmeta,
+                           const int4 *__restrict__ dmeta_u,
+                           const double *__restrict__ avals, const double *__restrict__ scale,
+                           double *__restrict__ dinv, const double *lval, const double *ut,
+                           double *udiag)
+{
+	constexpr int BS = 5, GPW = 6, BS2 = 25;
+	constexpr int A_BYTES = 208, RUN_BYTES = 624, GROUP_BYTES = A_BYTES + 2*RUN_BYTES;      // 1456
+	constexpr int STAGE_BYTES = GPW*GROUP_BYTES;                                            // 8736
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bars[4];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	unsigned char *const wsm = smem_raw + (size_t)w*STAGE_BYTES;
+	if(lane == 0) mbar_init(&bars[w], 1);
+	__syncwarp();
+	const long long warp = (long long)blockIdx.x*(blockDim.x >> 5) + w;
+	const long long stride = (long long)gridDim.x*(blockDim.x >> 5)*GPW;
+	const bool lanevalid = g < GPW;
+	long long t = warp*GPW + g;
+	const int4 none = make_int4(-1, 0, 0, 0);
+	auto getmeta = [&](const long long tt) { return (lanevalid && tt < nrows) ? __ldg(dmeta + tt) : none; };
+	auto getu = [&](const long long tt) { return (lanevalid && tt < nrows) ? __ldg(dmeta_u + tt) : none; };
+
+	int4 m0 = getmeta(t), m1 = getmeta(t + stride);           // {A entry, first L index, products, -}
+	int4 u0 = getu(t), u1 = getu(t + stride);                 // U indices of the products
+	const long long niter = (nrows + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		const int4 m2 = getmeta(t + 2*stride), u2 = getu(t + 2*stride);
+		const bool active = m0.x >= 0;
+		const int row = active ? (int)t : 0, nk = active ? m0.z : 0;
+		// lane 0 of every group copies the A block, lane 1 the L run, lanes 2.. the U partners
+		const int uidx = (r == 2) ? u0.x : (r == 3) ? u0.y : u0.z;
+		{
+			unsigned bytes = 0, dstoff = 0;
+			size_t a = 0;
+			if(active) {
+				if(r == 0) { a = (size_t)(avals + (size_t)m0.x*BS2); bytes = A_BYTES; }
+				else if(r == 1 && nk > 0) {
+					a = (size_t)(lval + (size_t)m0.y*BS2); dstoff = A_BYTES;
+					bytes = ((unsigned)(nk*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
+				}
+				else if(URUN && r == 2 && nk > 0) {
+					a = (size_t)(ut + (size_t)u0.x*BS2); dstoff = A_BYTES + RUN_BYTES;
+					bytes = ((unsigned)(nk*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
+				}
+				else if(!URUN && r >= 2 && r - 2 < nk) {
+					a = (size_t)(ut + (size_t)uidx*BS2); dstoff = A_BYTES + RUN_BYTES + (r - 2)*208;
+					bytes = 208;
+				}
+			}
+			const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+			if(lane == 0) mbar_expect_tx(&bars[w], total);
+			if(bytes)
+				bulk_g2s(wsm + (size_t)g*GROUP_BYTES + dstoff, (const void*)(a & ~(size_t)15), bytes, &bars[w]);
+		}
+		mbar_wait(&bars[w], (unsigned)(it & 1));
+
+		const unsigned char *gs = wsm + (size_t)g*GROUP_BYTES;
+		double sum[BS];
+#pragma unroll
+		for(int c = 0; c < BS; c++) sum[c] = 0;
+		if(active) {
+			const double *sa = reinterpret_cast<const double*>(gs) + ((((size_t)(avals + (size_t)m0.x*BS2)) & 15) >> 3);
+#pragma unroll
+			for(int c = 0; c < BS; c++) sum[c] = sa[c*BS + r];
+			if(SCALE) {
+				const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)row*BS + c);
+			}
+		}
+		const double *sl = reinterpret_cast<const double*>(gs + A_BYTES) + ((((size_t)(lval + (size_t)m0.y*BS2)) & 15) >> 3);
+		const int nkmax = __reduce_max_sync(0xffffffffu, nk);
+		for(int k = 0; k < nkmax; k++) {
+			double lr[BS], ur[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++) { lr[c] = 0; ur[c] = 0; }
+			if(k < nk) {
+				const double *su;
+				if(URUN) su = reinterpret_cast<const double*>(gs + A_BYTES + RUN_BYTES)
+					+ ((((size_t)(ut + (size_t)u0.x*BS2)) & 15) >> 3) + k*BS2;
+				else {
+					const int uk = (k == 0) ? u0.x : (k == 1) ? u0.y : u0.z;
+					su = reinterpret_cast<const double*>(gs + A_BYTES + RUN_BYTES + k*208)
+						+ ((((size_t)(ut + (size_t)uk*BS2)) & 15) >> 3);
+				}
+#pragma unroll
+				for(int c = 0; c < BS; c++) { lr[c] = sl[k*BS2 + c*BS + r]; ur[c] = su[c*BS + r]; }
+			}
+			group_mul_sub<BS>(sum, lr, ur, g*BS);
+		}
+		if(active) BlkIO<BS>::store_row(udiag + (size_t)row*BS2, r, sum);
+		{
+			double x[BS];
+			int prow;
+			group_inverse<BS>(sum, x, g*BS, r, prow);
+			if(active) BlkIO<BS>::store_row(dinv + (size_t)row*BS2, prow, x);
+		}
+		__syncwarp();                       // everybody has read the stage before it is refilled
+		m0 = m1; m1 = m2; u0 = u1; u1 = u2; t += stride;
+	}
+}
+
+/// The lower launch in the same form (IluPattern::lower_rows_ok: no lower entry has products, at
+/// most three lower entries per row): a group per ROW; per row one copy of the run of A blocks of
+/// its lower part and one 208-byte copy of U_jj^-1 per entry; L_ij = A_ij U_jj^-1 is stored to the
+/// run lval[l .. l+nl).
+template <bool SCALE>
+__global__ void __launch_bounds__(128)
+block5_lower_staged_kernel(const int nrows, const int4 *__restrict__ rmeta,
+                           const int4 *__restrict__ rcols, const double *__restrict__ avals,
+                           const double *__restrict__ scale, const double *__restrict__ dinv,
+                           double *lval)
+{
+	constexpr int BS = 5, GPW = 6, BS2 = 25;
+	constexpr int RUN_BYTES = 624, GROUP_BYTES = RUN_BYTES + 3*208;                         // 1248
+	constexpr int STAGE_BYTES = GPW*GROUP_BYTES;                                            // 7488
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bars[4];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	unsigned char *const wsm = smem_raw + (size_t)w*STAGE_BYTES;
+	if(lane == 0) mbar_init(&bars[w], 1);
+	__syncwarp();
+	const long long warp = (long long)blockIdx.x*(blockDim.x >> 5) + w;
+	const long long stride = (long long)gridDim.x*(blockDim.x >> 5)*GPW;
+	const bool lanevalid = g < GPW;
+	long long t = warp*GPW + g;
+	const int4 none = make_int4(0, 0, 0, 0);
+	auto getmeta = [&](const long long tt) { return (lanevalid && tt < nrows) ? __ldg(rmeta + tt) : none; };
+	auto getcols = [&](const long long tt) { return (lanevalid && tt < nrows) ? __ldg(rcols + tt) : none; };
+
+	int4 m0 = getmeta(t), m1 = getmeta(t + stride);           // {first A entry, first L index, entries, -}
+	int4 c0 = getcols(t), c1 = getcols(t + stride);
+	const long long niter = (nrows + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		const int4 m2 = getmeta(t + 2*stride), c2 = getcols(t + 2*stride);
+		const int nl = m0.z;
+		const int row = (int)t;
+		// lane 0 of every group copies the run of A blocks, lanes 1..3 the inverses U_jj^-1
+		const int col = (r == 1) ? c0.x : (r == 2) ? c0.y : c0.z;
+		{
+			unsigned bytes = 0, dstoff = 0;
+			size_t a = 0;
+			if(nl > 0) {
+				if(r == 0) {
+					a = (size_t)(avals + (size_t)m0.x*BS2);
+					bytes = ((unsigned)(nl*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
+				}
+				else if(r >= 1 && r - 1 < nl) {
+					a = (size_t)(dinv + (size_t)col*BS2); dstoff = RUN_BYTES + (r - 1)*208;
+					bytes = 208;
+				}
+			}
+			const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+			if(lane == 0) mbar_expect_tx(&bars[w], total);
+			if(bytes)
+				bulk_g2s(wsm + (size_t)g*GROUP_BYTES + dstoff, (const void*)(a & ~(size_t)15), bytes, &bars[w]);
+		}
+		mbar_wait(&bars[w], (unsigned)(it & 1));
+
+		const unsigned char *gs = wsm + (size_t)g*GROUP_BYTES;
+		const double *sa = reinterpret_cast<const double*>(gs) + ((((size_t)(avals + (size_t)m0.x*BS2)) & 15) >> 3);
+		const int nlmax = __reduce_max_sync(0xffffffffu, nl);
+		for(int e = 0; e < nlmax; e++) {
+			const bool has = e < nl;
+			const int ce = (e == 0) ? c0.x : (e == 1) ? c0.y : c0.z;
+			double s[BS], drow[BS];
+#pragma unroll
+			for(int c = 0; c < BS; c++) { s[c] = 0; drow[c] = 0; }
+			if(has) {
+				const double *sd = reinterpret_cast<const double*>(gs + RUN_BYTES + e*208)
+					+ ((((size_t)(dinv + (size_t)ce*BS2)) & 15) >> 3);
+#pragma unroll
+				for(int c = 0; c < BS; c++) { s[c] = sa[e*BS2 + c*BS + r]; drow[c] = sd[c*BS + r]; }
+				if(SCALE) {
+					const double sr = __ldg(scale + (size_t)row*BS + r);
+#pragma unroll
+					for(int c = 0; c < BS; c++) s[c] *= sr*__ldg(scale + (size_t)ce*BS + c);
+				}
+			}
+			double out[BS];
+			group_mul<BS>(out, s, drow, g*BS);                               // L = A_ij * U_jj^-1
+			if(has) BlkIO<BS>::store_row(lval + (size_t)(m0.y + e)*BS2, r, out);   // single final store
+		}
+		__syncwarp();                       // everybody has read the stage before it is refilled
+		m0 = m1; m1 = m2; c0 = c1; c1 = c2; t += stride;
+	}
+}
+
 // ------------------------------------------------------------------ exact block ILU(0), one launch
 
 __device__ __forceinline__ int ld_poll_flag(const int *p)
@@ -709,7 +920,26 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 	const long long per_cta = 8*GPW;
 	static const bool force_simple = getenv("B200_LOWER_SIMPLE") != nullptr;   // A/B switch (development)
 	const bool pipelined = (BS <= 4) && !force_simple;
-	if(pl.nlower > 0) {
+	static const bool no_staged_l = getenv("B200_NO_STAGED") != nullptr || getenv("B200_NO_STAGED_LOWER") != nullptr;
+	if(BS == 5 && pl.nlower > 0 && !changed && pl.lower_rows_ok && !no_staged_l) {
+		ProfScope ps(KC_FACTOR_LOWER, st);
+		constexpr int SMEM = 4*6*(624 + 3*208);
+		static int grid = 0;
+		if(!grid) {
+			int dev = 0, sms = 148, per = 1;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			B200_CUDA(cudaFuncSetAttribute(block5_lower_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			B200_CUDA(cudaFuncSetAttribute(block5_lower_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, block5_lower_staged_kernel<false>, 128, SMEM) != cudaSuccess || per < 1) per = 1;
+			grid = sms*per;
+		}
+		const int g = (int)std::max<long long>(1, std::min<long long>(grid, (A.nbrows + 23)/24));
+		if(scale) block5_lower_staged_kernel<true><<<g, 128, SMEM, st>>>(A.nbrows, pl.lrow_meta, pl.lrow_cols, A.vals, scale, dinv, F.lval.p);
+		else block5_lower_staged_kernel<false><<<g, 128, SMEM, st>>>(A.nbrows, pl.lrow_meta, pl.lrow_cols, A.vals, scale, dinv, F.lval.p);
+		B200_LAUNCHED();
+	}
+	else if(pl.nlower > 0) {
 		ProfScope ps(KC_FACTOR_LOWER, st);
 #define B200_LOWER(K)                                                                             \
 		{ auto k = K; k<<<persistent_grid(k, per_cta, pl.nlower), 256, 0, st>>>(pl.nlower, pl.slmeta, \
@@ -724,7 +954,35 @@ static void launch_block_sweep(const Mat& A, const IluPattern& pl, const double 
 #undef B200_LOWER
 		B200_LAUNCHED();
 	}
-	if(nup > 0) {
+	static const bool no_staged = getenv("B200_NO_STAGED") != nullptr;            // A/B switch (development)
+	if(BS == 5 && nup > 0 && !all_upper && !changed && pl.diag_runs_ok && !no_staged) {
+		// the diagonals are the only upper entries that change, their L partners are runs: rows
+		// staged in shared memory by TMA (block5_upper_staged_kernel)
+		ProfScope ps(KC_FACTOR_UPPER, st);
+		constexpr int SMEM = 4*6*(208 + 2*624);
+		const bool urun = F.ut.p && pl.diag_u_runs;
+		static int grid = 0;
+		if(!grid) {
+			int dev = 0, sms = 148, per = 1;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			B200_CUDA(cudaFuncSetAttribute(block5_upper_staged_kernel<true,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			B200_CUDA(cudaFuncSetAttribute(block5_upper_staged_kernel<false,true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			B200_CUDA(cudaFuncSetAttribute(block5_upper_staged_kernel<true,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			B200_CUDA(cudaFuncSetAttribute(block5_upper_staged_kernel<false,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+			if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, block5_upper_staged_kernel<false,false>, 128, SMEM) != cudaSuccess || per < 1) per = 1;
+			grid = sms*per;
+		}
+		const int g = (int)std::max<long long>(1, std::min<long long>(grid, (A.nbrows + 23)/24));
+		const double *usrc = F.ut.p ? F.ut.p : F.uval.p;
+#define B200_STAGED(SC, UR) block5_upper_staged_kernel<SC,UR><<<g, 128, SMEM, st>>>(A.nbrows, pl.dmeta, pl.dmeta_u, \
+			A.vals, scale, dinv, F.lval.p, usrc, F.udiag.p)
+		if(urun) { if(scale) B200_STAGED(true, true); else B200_STAGED(false, true); }
+		else { if(scale) B200_STAGED(true, false); else B200_STAGED(false, false); }
+#undef B200_STAGED
+		B200_LAUNCHED();
+	}
+	else if(nup > 0) {
 		ProfScope ps(KC_FACTOR_UPPER, st);
 		// the diagonal entries refresh U_ii^-1 inside this launch by the cooperative Gauss-Jordan
 		// of blockops.cuh::group_inverse (one row per lane: 64 registers, 4 CTAs/SM).  The

@@ -175,6 +175,53 @@ __global__ void invert_order_kernel(const long long n, const int *__restrict__ o
 	if(d < n) pos[order[d]] = (int)d;
 }
 
+/// Per row, for the staged bs = 5 upper launch: dmeta = {entry of A, first L index, products, 0} of
+/// the diagonal entry, dmeta_u = the U indices of its (at most 3) products.  bad[0] is raised unless
+/// every diagonal entry has at most nkmax products whose L partners are the run l, l+1, ...; bad[1]
+/// unless the U partners are a run as well (column-ordered U copy).
+__global__ void __launch_bounds__(256)
+diag_runs_kernel(const int nbrows, const int *__restrict__ uptr, const int4 *__restrict__ uall,
+                 const int2 *__restrict__ spairs, const int nkmax, int4 *__restrict__ dmeta,
+                 int4 *__restrict__ dmeta_u, int *__restrict__ bad)
+{
+	const int row = blockIdx.x*blockDim.x + threadIdx.x;
+	if(row >= nbrows) return;
+	const int4 m = uall[uptr[row] + row];            // the diagonal is the first upper entry of its row
+	const int nk = m.z - m.y;
+	bool ok = (m.w == ~row) && nk <= nkmax, urun = true;
+	int u[3] = {0, 0, 0};
+	int lfirst = 0;
+	if(ok && nk > 0) {
+		const int2 first = spairs[m.y];
+		lfirst = first.x; u[0] = first.y;
+		for(int k = 1; k < nk; k++) {
+			const int2 p = spairs[m.y + k];
+			ok &= (p.x == first.x + k);
+			urun &= (p.y == first.y + k);
+			if(k < 3) u[k] = p.y;
+		}
+	}
+	if(!ok) bad[0] = 1;
+	if(!urun) bad[1] = 1;
+	dmeta[row] = make_int4(m.x, lfirst, nk, 0);
+	dmeta_u[row] = make_int4(u[0], u[1], u[2], 0);
+}
+
+/// Per row, for the staged bs = 5 lower launch: {first A entry of the row, first L index, lower
+/// entries, 0} and the columns of the (at most 3) lower entries
+__global__ void __launch_bounds__(256)
+lower_rows_kernel(const int nbrows, const int *__restrict__ browptr, const int *__restrict__ lptr,
+                  const int *__restrict__ lcol, int4 *__restrict__ meta, int4 *__restrict__ cols)
+{
+	const int row = blockIdx.x*blockDim.x + threadIdx.x;
+	if(row >= nbrows) return;
+	const int lb = lptr[row], nl = lptr[row+1] - lb;
+	int c[3] = {0, 0, 0};
+	for(int e = 0; e < nl && e < 3; e++) c[e] = lcol[lb + e];
+	meta[row] = make_int4(browptr[row], lb, nl, 0);
+	cols[row] = make_int4(c[0], c[1], c[2], 0);
+}
+
 /// blocks: destinations of the strict upper entries move to the column-major copy
 __global__ void upper_dest_transposed_kernel(const long long n, int4 *__restrict__ uall,
                                              const int *__restrict__ utpos)
@@ -284,8 +331,7 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 			const int *utpos = nullptr;
 			static const bool want_ut = getenv("B200_UT") != nullptr;   // A/B switch (development)
 			if(A.bs == 5 && want_ut) {
-				// OPTIONAL (off: measured no faster while the launches are bound by the L1 data pipe).
-				// Block factors keep a second copy of the strict upper part in COLUMN order (UT): the
+				// OPTIONAL: block factors keep a second copy of the strict upper part in COLUMN order (UT): the
 				// U_kj partners of a product then sit next to each other - for a diagonal entry
 				// (i,i) of a structurally symmetric matrix the run UT[column i] is index-aligned with
 				// the run L[row i], so the dominant products stream instead of gathering 200-byte
@@ -348,6 +394,40 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 			B200_CUDA(cudaMemcpyAsync(&nsel, d_nsel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 			B200_CUDA(cudaStreamSynchronize(st));
 			pl.nuwork = nsel;
+		}
+	}
+	// bs = 5, column-ordered U copy present: are the products of every diagonal entry index-aligned
+	// runs (pairs (l+k, u+k)) of at most 3 blocks, and are the diagonals the only upper entries that
+	// change?  Then the upper launch can stage whole runs with TMA (factor.cu, "staged").
+	pl.diag_runs_ok = pl.diag_u_runs = false;
+	if(A.bs == 5 && pl.nuwork == A.nbrows && A.nbrows > 0) {
+		pl.dmeta.alloc(A.nbrows);
+		pl.dmeta_u.alloc(A.nbrows);
+		DevBuf<int> d_bad;
+		d_bad.alloc(2);
+		B200_CUDA(cudaMemsetAsync(d_bad, 0, 2*sizeof(int), st));
+		diag_runs_kernel<<<div_up(A.nbrows, 256), 256, 0, st>>>(A.nbrows, pl.uptr, pl.suall, pl.spairs, 3,
+		                                                      pl.dmeta, pl.dmeta_u, d_bad);
+		B200_LAUNCHED();
+		int bad[2] = {1, 1};
+		B200_CUDA(cudaMemcpyAsync(bad, d_bad.p, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+		B200_CUDA(cudaStreamSynchronize(st));
+		pl.diag_runs_ok = (bad[0] == 0);
+		pl.diag_u_runs = (bad[0] == 0 && bad[1] == 0);
+		if(!pl.diag_runs_ok) { pl.dmeta.release(); pl.dmeta_u.release(); }
+	}
+	// ... and the lower launch, when no lower entry has products and no row more than 3 lower entries
+	pl.lower_rows_ok = false;
+	if(A.bs == 5 && A.nbrows > 0 && pl.max_lower_len <= 3 && pl.nlower > 0) {
+		long long stats[5];
+		pattern_stats(pl, stats, st);
+		if(stats[3] == 0) {
+			pl.lrow_meta.alloc(A.nbrows);
+			pl.lrow_cols.alloc(A.nbrows);
+			lower_rows_kernel<<<div_up(A.nbrows, 256), 256, 0, st>>>(A.nbrows, A.browptr, pl.lptr, pl.lcol,
+			                                                       pl.lrow_meta, pl.lrow_cols);
+			B200_LAUNCHED();
+			pl.lower_rows_ok = true;
 		}
 	}
 	B200_CUDA(cudaStreamSynchronize(st));

@@ -133,3 +133,56 @@ def test_runsolvetest_driver(tmp_path):
                                   "--mat_type", "csr"]) == 0
     assert testsolve.main(base + ["--solver_type", "fgmres", "--preconditioner_type", "seqilu0",
                                   "--mat_type", "bsr", "--storage_order", "rowmajor"]) == 0
+
+
+@pytest.mark.parametrize("solver", ["gcr", "fgmres"])
+def test_in_place_preconditioner_starts_from_zero_in_every_solve(solver):
+    """The chaotic GS relaxation used as a preconditioner sweeps in place on whatever its output
+    vector holds on entry (relaxation_chaotic.cpp:22-45).  The restarted drivers keep their work
+    vectors between solves; like the reference's value-initialised vectors (tests/solvers.cpp:264-270)
+    they must start from zero in every solve: two consecutive solves give the same iteration count
+    and the same (finite) solution."""
+    import torch
+    m = case("2dcyl1_bsr4")
+    view = bb.SRMatrixView(m)
+    p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["gs"], bs=4, napplysweeps=3))
+    p.compute()
+    b = torch.from_numpy(golden_matrices()["2dcyl1_b"]).cuda()
+    runs = []
+    for rep in range(2):
+        sol = bb.GCR(view, p, 30) if solver == "gcr" else bb.FGMRES(view, p, 30)
+        sol.setParams(1e-8, 2000)
+        x = torch.zeros_like(b)
+        info = sol.solve(b, x)
+        assert info.converged and bool(torch.isfinite(x).all())
+        runs.append((info.iters, x.cpu().numpy()))
+    # asynchronous sweeps: counts agree to a few iterations, solutions to the solve tolerance
+    assert abs(runs[0][0] - runs[1][0]) <= max(2, runs[0][0]//10), (runs[0][0], runs[1][0])
+    assert relerr(runs[0][1], runs[1][1]) < 1e-5
+
+
+def test_solve_rejects_mismatched_streams_and_reports_deferred_errors():
+    """b200_solve refuses a preconditioner and a matrix on different streams (their launches would
+    not be ordered); b200_prec_check reports nothing after healthy applies."""
+    import ctypes as C
+    import torch
+    from blasted_b200._lib import lib
+    m = case("2dcyl1_csr")
+    view = bb.SRMatrixView(m)
+    p = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["seqilu0"], bs=1))
+    p.compute()
+    r = torch.from_numpy(golden_outputs()["2dcyl1_csr_r"]).cuda()
+    z = torch.empty_like(r)
+    p.apply(r, z)
+    assert lib.b200_prec_check(p._h) == 0
+    st = torch.cuda.Stream()
+    lib.b200_prec_set_stream(p._h, C.c_void_p(st.cuda_stream))
+    sol = bb.GCR(view, p, 30)
+    sol.setParams(1e-8, 100)
+    with pytest.raises(RuntimeError, match="different streams"):
+        sol.solve(r, torch.zeros_like(r))
+    lib.b200_prec_set_stream(p._h, C.c_void_p(0))
+    info = sol.solve(r, torch.zeros_like(r))
+    assert info.converged

@@ -79,12 +79,15 @@ gather_flat(const long long M, const int *__restrict__ idx, const double *__rest
 	}
 }
 
-// one TMA bulk copy (208 B) per block into shared memory, S stages of NB blocks per CTA
-template <int S, int NB>
+// one TMA bulk copy (BYTES per copy) into shared memory, S stages of NB copies per CTA; the index of
+// the copy a thread will issue next is prefetched one iteration ahead (no dependent global load in
+// the issue path), so that the measured rate is the TMA unit's, not the index latency's
+template <int S, int NB, int BYTES>
 __global__ void __launch_bounds__(256)
 gather_tma(const long long M, const int *__restrict__ idx, const double *__restrict__ data, double *__restrict__ out)
 {
-	constexpr int SLOT = 208;
+	constexpr int SLOT = BYTES;
+	constexpr int BPC = BYTES/208;                 // blocks per copy (runs of consecutive blocks)
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ __align__(8) unsigned long long full[S];
 	__shared__ int soff[S][NB];
@@ -94,43 +97,51 @@ gather_tma(const long long M, const int *__restrict__ idx, const double *__restr
 	}
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
+	const long long ncopies = M/BPC;
 	const long long stride = (long long)gridDim.x*NB;
 	const long long base = (long long)blockIdx.x*NB;
-	const long long niter = (M + stride - 1)/stride;
-	auto issue = [&](long long it, int s) {
-		// expected bytes first (thread 0), then one copy per slot
+	const long long niter = (ncopies + stride - 1)/stride;
+	auto fetch = [&](long long it) -> int {
+		const long long t = base + it*stride + tid;
+		return (tid < NB && t < ncopies) ? __ldg(idx + t*BPC) : -1;
+	};
+	auto issue = [&](long long it, int s, int myidx) {
 		const long long t0 = base + it*stride;
-		const int cnt = (int)max(0LL, min((long long)NB, M - t0));
+		const int cnt = (int)max(0LL, min((long long)NB, ncopies - t0));
 		if(tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 		                          :: "r"(smem_u32(&full[s])), "r"(cnt*SLOT) : "memory");
-		__syncwarp();
 		if(tid < cnt) {
-			const size_t a = (size_t)(data + (size_t)__ldg(idx + t0 + tid)*25);
+			const size_t a = (size_t)(data + (size_t)myidx*25);
 			soff[s][tid] = (int)(a & 15) >> 3;
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 			             :: "r"(smem_u32(smem + ((size_t)s*NB + tid)*SLOT)), "l"(a & ~(size_t)15), "r"(SLOT),
 			                "r"(smem_u32(&full[s])) : "memory");
 		}
 	};
-	// NB <= 64: warps 0,1 issue
-	for(int s = 0; s < S && s < niter; s++) { if(tid < 64) issue(s, s); }
+	for(int s = 0; s < S && s < niter; s++) { const int i0 = fetch(s); if(tid < 64) issue(s, s, i0); }
+	int nxt = fetch(S);
 	const int lane = tid & 31, w = tid >> 5, g = lane/5, r = lane - g*5;
 	for(long long it = 0; it < niter; it++) {
 		const int s = (int)(it % S);
 		const unsigned parity = (unsigned)((it / S) & 1);
+		const int nxt2 = fetch(it + S + 1);
 		asm volatile("{\n.reg .pred p;\nW1:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D1;\nbra W1;\nD1:\n}\n"
 		             :: "r"(smem_u32(&full[s])), "r"(parity) : "memory");
+		// consume: every group sums one block (the first of its copy when BPC > 1 - enough to keep the loads honest)
 		const int slot = w*6 + g;
 		const long long t = base + it*stride + slot;
-		if(g < 6 && slot < NB && t < M) {
+		if(g < 6 && slot < NB && t < ncopies) {
 			const double *b = (const double*)(smem + ((size_t)s*NB + slot)*SLOT) + soff[s][slot];
 			double sum = 0;
 #pragma unroll
-			for(int c = 0; c < 5; c++) sum += b[c*5 + r];
+			for(int q = 0; q < BPC; q++)
+#pragma unroll
+				for(int c = 0; c < 5; c++) sum += b[q*25 + c*5 + r];
 			out[t*5 + r] = sum;
 		}
 		__syncthreads();
-		if(it + S < niter && tid < 64) issue(it + S, s);
+		if(it + S < niter && tid < 64) issue(it + S, s, nxt);
+		nxt = nxt2;
 	}
 }
 
@@ -162,20 +173,13 @@ int main(int argc, char **argv)
 		run("rows + prefetch.global.L2", [&] { gather_rows<1><<<148*4, 256>>>(M, idx, data, out); });
 		run("rows + bulk prefetch L2", [&] { gather_rows<2><<<148*4, 256>>>(M, idx, data, out); });
 		run("flat 25 lanes/block", [&] { gather_flat<<<148*6, 256>>>(M, idx, data, out); });
-		{
-			constexpr int S = 4, NB = 48;
-			auto k = gather_tma<S,NB>;
-			const int sm = S*NB*208;
-			CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-			run("TMA 208B/block S=4 x4CTA", [&] { k<<<148*4, 256, sm>>>(M, idx, data, out); });
-		}
-		{
-			constexpr int S = 8, NB = 48;
-			auto k = gather_tma<S,NB>;
-			const int sm = S*NB*208;
-			CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-			run("TMA 208B/block S=8 x2CTA", [&] { k<<<148*2, 256, sm>>>(M, idx, data, out); });
-		}
+#define TMA_RUN(SV, NBV, BYTESV, CTAS, LABEL) { auto k = gather_tma<SV,NBV,BYTESV>; const int sm = SV*NBV*BYTESV; \
+		CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+		run(LABEL, [&] { k<<<148*CTAS, 256, sm>>>(M, idx, data, out); }); }
+		TMA_RUN(4, 48, 208, 4, "TMA 208B S=4 x4CTA (idx pf)")
+		TMA_RUN(8, 48, 208, 2, "TMA 208B S=8 x2CTA (idx pf)")
+		TMA_RUN(3, 48, 624, 2, "TMA 624B(3 blk) S=3 x2CTA")
+		TMA_RUN(2, 48, 624, 3, "TMA 624B(3 blk) S=2 x3CTA")
 	}
 	return 0;
 }
