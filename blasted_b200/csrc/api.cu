@@ -495,7 +495,16 @@ int b200_prec_apply_host(b200_prec *p, const double *r, double *z)
 		Prec& P = p->p;
 		const size_t n = P.dim();
 		P.hr.alloc(n); P.hz.alloc(n);
-		B200_CUDA(cudaMemcpyAsync(P.hr, r, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
+		// r travels on a copy stream of its own: an asynchronous compute() enqueued just before
+		// (the usual PCSetUp -> PCApply order) keeps the SMs busy while the link carries r
+		// (pinned r; a pageable one is staged by the driver and gains nothing)
+		if(!P.copy_stream) {
+			B200_CUDA(cudaStreamCreateWithFlags(&P.copy_stream, cudaStreamNonBlocking));
+			B200_CUDA(cudaEventCreateWithFlags(&P.ev_copy, cudaEventDisableTiming));
+		}
+		B200_CUDA(cudaMemcpyAsync(P.hr, r, n*sizeof(double), cudaMemcpyHostToDevice, P.copy_stream));
+		B200_CUDA(cudaEventRecord(P.ev_copy, P.copy_stream));
+		B200_CUDA(cudaStreamWaitEvent(P.stream, P.ev_copy, 0));
 		if(P.s.prectype == B200_GS || (P.s.prectype == B200_SGS && P.s.apply_inittype == B200_INIT_A_NONE))
 			B200_CUDA(cudaMemcpyAsync(P.hz, z, n*sizeof(double), cudaMemcpyHostToDevice, P.stream));
 		prec_apply(P, P.hr, P.hz);
@@ -549,6 +558,8 @@ void b200_prec_destroy(b200_prec *p)
 	if(p->p.ev1) cudaEventDestroy(p->p.ev1);
 	if(p->p.evc0) cudaEventDestroy(p->p.evc0);
 	if(p->p.evc1) cudaEventDestroy(p->p.evc1);
+	if(p->p.ev_copy) cudaEventDestroy(p->p.ev_copy);
+	if(p->p.copy_stream) cudaStreamDestroy(p->p.copy_stream);
 	for(void *g : p->p.level_graph) if(g) cudaGraphExecDestroy((cudaGraphExec_t)g);
 	if(p->p.cap_stream) cudaStreamDestroy(p->p.cap_stream);
 	delete p;

@@ -26,6 +26,7 @@
  */
 #include "common.cuh"
 #include "blockops.cuh"
+#include "tma.cuh"
 
 namespace b200 {
 
@@ -40,6 +41,7 @@ struct TriDev {
 	const int *rows;
 	int row_begin, row_end;
 	int descending;
+	int max_part_len;                        ///< longest row part of this sweep, 0 = unknown
 };
 
 template <int KIND>
@@ -267,6 +269,176 @@ tri_block_pipe_kernel(const TriDev a)
 	}
 }
 
+// ------------------------------------------------------------------ bs = 5 sweeps, staged
+//
+// tri_block_kernel<5> is latency-bound (ncu: L1 data pipe 58-64 %, long-scoreboard stalls): a group
+// reads every 200-byte block as five 40-byte segments and every x segment as five broadcast loads.
+// Where no row part has more than three blocks (every face-neighbour block stencil) the sweep is
+// staged like the factor launches (factor.cu, "staged"): a warp owns six consecutive rows per
+// iteration, lane 0 of every group copies the row's run of blocks and lane 1 the inverted diagonal
+// block into shared memory with TMA bulk copies on the warp's mbarrier, and while they fly the lanes
+// fetch the column indices, ONE x entry per lane and block (lane c needs x_c only: it multiplies
+// column c of every block, read as 40 contiguous bytes from shared memory) and the right-hand
+// side.  The five partial vectors of a group are summed once per row (4 shuffles per lane), the
+// product with the inverted diagonal block is formed the same way.  One final store per row, x
+// gathered with relaxed L2 loads, rows ascending (lower/forward) or descending (upper/backward):
+// the chaotic-iteration rules of the generic kernel.  Summation order differs from the generic
+// kernel at rounding level only.
+
+/// y_r = sum over the group's lanes c of v_c[r]  (v = this lane's partial vector)
+template <int BS>
+__device__ __forceinline__ double group_reduce_columns(const double (&v)[BS], const int gbase, const int r)
+{
+	double y = pick<BS>(v, r);
+#pragma unroll
+	for(int t = 1; t < BS; t++) {
+		const double x = pick<BS>(v, (r - t + BS) % BS);       // what lane (r-t) wants from this lane
+		y += __shfl_sync(0xffffffffu, x, min(gbase + (r + t) % BS, 31));
+	}
+	return y;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+tri5_staged_kernel(const TriDev a)
+{
+	constexpr int BS = 5, GPW = 6, BS2 = 25, K = 3;
+	// the six rows of a warp are consecutive, so their parts are ONE contiguous span of the (split
+	// or matrix-ordered) value array when the parts are whole rows of a split array, and their
+	// inverted diagonal blocks one span of the compact array: two copies per warp and iteration
+	constexpr int SLOT_BYTES = K*BS2*8 + 24;                                               // 624: one row's run
+	constexpr int RUN_BYTES = GPW*SLOT_BYTES, D_BYTES = GPW*BS2*8 + 16;                    // 3744, 1216
+	constexpr int STAGE_BYTES = RUN_BYTES + D_BYTES;                                       // 4960
+	constexpr bool NEED_D = (KIND != TRI_ILU_LOWER);
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) unsigned long long bars[4];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int g = lane / BS, r = lane - g*BS;
+	unsigned char *const wsm = smem_raw + (size_t)w*STAGE_BYTES;
+	if(lane == 0) mbar_init(&bars[w], 1);
+	__syncwarp();
+	const long long warp = (long long)blockIdx.x*(blockDim.x >> 5) + w;
+	const long long stride = (long long)gridDim.x*(blockDim.x >> 5)*GPW;
+	const int nrows = a.row_end - a.row_begin;
+	const int *const cols_arr = a.part_ptr ? a.part_col : a.bcolind;
+	const bool spans = a.part_ptr != nullptr;            // parts of consecutive rows are adjacent
+	auto rowof = [&](const long long tt) { return a.descending ? a.row_end - 1 - (int)tt : a.row_begin + (int)tt; };
+	auto load_meta = [&](const long long tt, int& js, int& je) {
+		js = 0; je = 0;
+		if(g < GPW && tt < nrows) {
+			const int row = rowof(tt);
+			if(a.part_ptr) { js = __ldg(a.part_ptr + row); je = __ldg(a.part_ptr + row + 1); }
+			else {
+				const int s = __ldg(a.browptr + row), e = __ldg(a.browptr + row + 1);
+				part_range<KIND>(s, __ldg(a.diagind + row), e, js, je);
+			}
+		}
+	};
+	long long t = warp*GPW + g;
+	int js0, je0, js1, je1;
+	load_meta(t, js0, je0);
+	load_meta(t + stride, js1, je1);
+	const long long niter = ((long long)nrows + stride - 1)/stride;
+	for(long long it = 0; it < niter; it++) {
+		int js2, je2;
+		load_meta(t + 2*stride, js2, je2);
+		const bool valid = (g < GPW) && (t < nrows);
+		const int row = valid ? rowof(t) : 0;
+		const int nb = je0 - js0;
+		// spans of the warp's rows
+		const int first = __reduce_min_sync(0xffffffffu, valid ? js0 : 0x7fffffff);
+		const int last = __reduce_max_sync(0xffffffffu, valid ? je0 : 0);
+		const int rmin = __reduce_min_sync(0xffffffffu, valid ? row : 0x7fffffff);
+		const int rmax = __reduce_max_sync(0xffffffffu, valid ? row : -1);
+		unsigned myoff = 0;                                  // byte offset of this group's run in the staged area
+		{
+			unsigned bytes = 0, dstoff = 0;
+			size_t src = 0;
+			if(spans) {
+				const size_t s0 = (size_t)(a.vals + (size_t)first*BS2);
+				myoff = (unsigned)((size_t)(js0 - first)*BS2*8 + (s0 & 15));
+				if(lane == 0 && last > first) { src = s0; bytes = ((unsigned)((last - first)*BS2*8) + (unsigned)(s0 & 15) + 15u) & ~15u; }
+			} else {
+				// matrix-ordered values (SGS on A): one run per row, K blocks of room each
+				const size_t s0 = (size_t)(a.vals + (size_t)js0*BS2);
+				if(valid && r == 0 && nb > 0) {
+					src = s0; dstoff = (unsigned)(g*SLOT_BYTES);
+					bytes = ((unsigned)(nb*BS2*8) + (unsigned)(s0 & 15) + 15u) & ~15u;
+				}
+				myoff = (unsigned)(g*SLOT_BYTES) + (unsigned)(s0 & 15);
+			}
+			if(NEED_D && lane == 1 && rmax >= rmin) {
+				src = (size_t)(a.dinv + (size_t)rmin*BS2); dstoff = RUN_BYTES;
+				bytes = ((unsigned)((rmax - rmin + 1)*BS2*8) + (unsigned)(src & 15) + 15u) & ~15u;
+			}
+			const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+			if(lane == 0) mbar_expect_tx(&bars[w], total);
+			if(bytes) bulk_g2s(wsm + dstoff, (const void*)(src & ~(size_t)15), bytes, &bars[w]);
+		}
+		// while the copies fly: column indices, this lane's x entries, the right-hand side
+		double xk[K];
+#pragma unroll
+		for(int k = 0; k < K; k++) {
+			xk[k] = 0;
+			if(valid && k < nb) xk[k] = ld_iter(a.xsrc + (size_t)__ldg(cols_arr + js0 + k)*BS + r);
+		}
+		double rhs = 0;
+		if(valid) {
+			rhs = __ldg(a.rhs + (size_t)row*BS + r);
+			if(a.rscale) rhs *= __ldg(a.rscale + (size_t)row*BS + r);
+		}
+		mbar_wait(&bars[w], (unsigned)(it & 1));
+
+		const double *sv = reinterpret_cast<const double*>(wsm + myoff);
+		double acc[BS];
+#pragma unroll
+		for(int i = 0; i < BS; i++) acc[i] = 0;
+		if(valid) {
+#pragma unroll
+			for(int k = 0; k < K; k++)
+				if(k < nb) {
+#pragma unroll
+					for(int i = 0; i < BS; i++) acc[i] = fma(sv[k*BS2 + r*BS + i], xk[k], acc[i]);   // column r of block k
+				}
+		}
+		const double y = group_reduce_columns<BS>(acc, g*BS, r);          // (sum_j V_ij x_j)_r
+		double out;
+		if(KIND == TRI_ILU_LOWER) out = rhs - y;
+		else {
+			const double tv = (KIND == TRI_SGS_BWD) ? y : rhs - y;
+			const size_t d0 = (size_t)(a.dinv + (size_t)(rmax >= rmin ? rmin : 0)*BS2);
+			const double *sd = reinterpret_cast<const double*>(wsm + RUN_BYTES + (d0 & 15)) + (size_t)(valid ? row - rmin : 0)*BS2;
+			double p[BS];
+#pragma unroll
+			for(int i = 0; i < BS; i++) p[i] = valid ? sd[r*BS + i]*tv : 0.0;   // column r of D^-1 times t_r
+			const double prod = group_reduce_columns<BS>(p, g*BS, r);
+			out = (KIND == TRI_SGS_BWD) ? rhs - prod : prod;
+		}
+		if(valid) a.x[(size_t)row*BS + r] = out;
+		__syncwarp();                       // everybody has read the stage before it is refilled
+		js0 = js1; je0 = je1; js1 = js2; je1 = je2;
+		t += stride;
+	}
+}
+
+template <int KIND>
+static void launch_tri5_staged(const TriDev& d, cudaStream_t st)
+{
+	constexpr int SMEM = 4*(6*624 + 6*25*8 + 16);
+	static int grid = 0;
+	if(!grid) {
+		int dev = 0, sms = 148, per = 1;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, tri5_staged_kernel<KIND>, 128, SMEM) != cudaSuccess || per < 1)
+			per = 1;
+		grid = sms*per;
+	}
+	const long long nrows = d.row_end - d.row_begin;
+	const int g = (int)std::max<long long>(1, std::min<long long>(grid, (nrows + 23)/24));
+	tri5_staged_kernel<KIND><<<g, 128, SMEM, st>>>(d);
+}
+
 /// Resident CTAs of a persistent kernel over all SMs (cached per kernel), capped by the work
 template <typename Kern>
 static int resident_grid(Kern kernel, long long rows_per_cta, long long nrows)
@@ -289,7 +461,8 @@ static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cu
 {
 	const long long nrows = d.row_end - d.row_begin;
 	if(nrows <= 0) return;
-	static const bool one_shot = getenv("B200_TRI1") != nullptr;      // A/B switch (development)
+	static const bool one_shot = getenv("B200_TRI1") != nullptr;      // A/B switches (development)
+	static const bool no_staged = getenv("B200_NO_STAGED") != nullptr || getenv("B200_NO_STAGED_TRI") != nullptr;
 	if(A.bs == 1) {
 #define B200_TRI_CASE(L)                                                           \
 		{                                                                          \
@@ -316,6 +489,9 @@ static void launch_kind(const Mat& A, const TriDev& d, const double avg_part, cu
 		else
 			tri_block_kernel<4,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
 	}
+	else if(A.bs == 5 && KIND != TRI_RELAX && !d.rows && d.max_part_len >= 1 && d.max_part_len <= 3 && !no_staged) {
+		launch_tri5_staged<KIND>(d, st);
+	}
 	else if(A.bs == 5) {
 		const long long nwarps = (nrows + 5)/6;
 		tri_block_kernel<5,KIND,false><<<div_up(nwarps*32, 256), 256, 0, st>>>(d);
@@ -332,6 +508,7 @@ void launch_tri_sweep(const Mat& A, TriKind kind, const TriArgs& a, cudaStream_t
 	d.vals = a.vals; d.dinv = a.dinv; d.rhs = a.rhs; d.rscale = a.rscale;
 	d.xsrc = a.xsrc ? a.xsrc : a.x; d.x = a.x; d.rows = a.rows;
 	d.row_begin = a.row_begin; d.row_end = a.row_end; d.descending = a.descending ? 1 : 0;
+	d.max_part_len = a.max_part_len;
 	const double half = 0.5*(A.avg_row_len - 1.0);
 	ProfScope ps((kind == TRI_ILU_LOWER || kind == TRI_SGS_FWD) ? KC_TRI_LOWER :
 	             (kind == TRI_ILU_UPPER || kind == TRI_SGS_BWD) ? KC_TRI_UPPER : KC_OTHER, st);
@@ -555,6 +732,7 @@ void launch_tri_syncfree(const Mat& A, TriKind kind, const TriArgs& a, int *tick
 	d.vals = a.vals; d.dinv = a.dinv; d.rhs = a.rhs; d.rscale = a.rscale;
 	d.xsrc = a.x; d.x = a.x; d.rows = a.rows;
 	d.row_begin = a.row_begin; d.row_end = a.row_end; d.descending = a.descending ? 1 : 0;
+	d.max_part_len = 0;
 	ProfScope ps((kind == TRI_ILU_LOWER || kind == TRI_SGS_FWD) ? KC_TRI_LOWER : KC_TRI_UPPER, st);
 	switch(kind) {
 	case TRI_ILU_LOWER: launch_syncfree_kind<TRI_ILU_LOWER>(A, d, ticket, err, st); break;

@@ -180,6 +180,16 @@ __device__ __forceinline__ void group_mul(double (&out)[BS], const double (&srow
 	}
 }
 
+/// v[idx] with a lane-dependent idx (a chain of selects; the array stays in registers)
+template <int BS>
+__device__ __forceinline__ double pick(const double (&v)[BS], const int idx)
+{
+	double x = v[0];
+#pragma unroll
+	for(int i = 1; i < BS; i++) x = (idx == i) ? v[i] : x;
+	return x;
+}
+
 /// Whether the device stores blocks of this size row-major
 inline bool device_rowmajor(const int bs) { return bs == 4; }
 

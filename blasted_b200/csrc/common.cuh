@@ -201,12 +201,14 @@ struct IluPattern {
 };
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st);
 void pattern_stats(const IluPattern& pl, long long out[5], cudaStream_t st);
+/// {longest strict lower row part, longest strict upper row part} of a matrix with diagonals
+void part_max_lengths(const Mat& A, int out[2], cudaStream_t st);
 /// Scalar matrices: only the split CSR structure (lptr/lcol/uptr/ucol, lentry/uentry, part lengths),
 /// for sweeps over A itself (SGS); no ILU position lists.
 void build_split_csr(const Mat& A, IluPattern& pl, cudaStream_t st);
-/// lval[t] = vals[lentry[t]], uval[t] = vals[uentry[t]]
+/// lval[t] = vals[lentry[t]], uval[t] = vals[uentry[t]]  (scalars, or bs x bs blocks)
 void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
-                         cudaStream_t st);
+                         cudaStream_t st, int bs = 1);
 
 /// Values of the ILU(0) factor in split form (see IluPattern): scalars, or bs x bs blocks
 struct ScalarFactor {
@@ -304,6 +306,7 @@ struct TriArgs {
 	const int *rows = nullptr;       ///< optional explicit row list (level scheduling)
 	int row_begin = 0, row_end = 0;  ///< range of rows (or of positions in `rows`)
 	bool descending = false;         ///< map CTAs to rows in descending order
+	int max_part_len = 0;            ///< longest row part of this sweep (0 = unknown): selects the staged bs = 5 kernel
 	// scalar split form (bs == 1 ILU): the part to sweep as its own CSR arrays; vals indexes it
 	const int *part_ptr = nullptr, *part_col = nullptr;
 	const double *part_diag = nullptr;
@@ -371,6 +374,8 @@ struct Prec {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;      ///< around the last apply()
 	cudaEvent_t evc0 = nullptr, evc1 = nullptr;    ///< around the last compute() (read lazily)
 	bool compute_timed = false;
+	cudaStream_t copy_stream = nullptr;            ///< host-pointer apply: r is uploaded beside a running compute()
+	cudaEvent_t ev_copy = nullptr;
 	double compute_ms = 0, apply_ms = 0;
 	// level-scheduled applies replayed as CUDA graphs (precond.cu::run_level_graph)
 	DevBuf<double> lev_r, lev_z;
@@ -378,6 +383,7 @@ struct Prec {
 	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
 	DevBuf<int> sync_flags;                           ///< {ticket, error} of the one-launch exact solves
 	DevBuf<int> rowdone;                              ///< per-row flags of the one-launch exact factorisation
+	int a_max_lower = 0, a_max_upper = 0;             ///< longest row parts of A (block SGS sweeps)
 	DevBuf<int> exact_slots;                          ///< blocks: level-sorted rows, levels padded to whole warps
 	int n_exact_slots = 0;
 

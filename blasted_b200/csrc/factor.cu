@@ -588,8 +588,10 @@ block5_upper_staged_kernel(const int nrows, const int4 *__restrict__ dmeta,
                            double *udiag)
 {
 	constexpr int BS = 5, GPW = 6, BS2 = 25;
-	constexpr int A_BYTES = 208, RUN_BYTES = 624, GROUP_BYTES = A_BYTES + 2*RUN_BYTES;      // 1456
-	constexpr int STAGE_BYTES = GPW*GROUP_BYTES;                                            // 8736
+	// per warp: six group areas {A block, U partners} and one L area for the runs of all six rows
+	constexpr int A_BYTES = 208, RUN_BYTES = 624, GROUP_BYTES = A_BYTES + RUN_BYTES;         // 832
+	constexpr int L_AREA = GPW*GROUP_BYTES;                                                 // 4992
+	constexpr int STAGE_BYTES = L_AREA + GPW*RUN_BYTES;                                     // 8736
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bars[4];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -612,30 +614,48 @@ block5_upper_staged_kernel(const int nrows, const int4 *__restrict__ dmeta,
 		const int4 m2 = getmeta(t + 2*stride), u2 = getu(t + 2*stride);
 		const bool active = m0.x >= 0;
 		const int row = active ? (int)t : 0, nk = active ? m0.z : 0;
-		// lane 0 of every group copies the A block, lane 1 the L run, lanes 2.. the U partners
+		// lane 0 of every group copies the A block, lanes 2.. the U partners; the L runs of the
+		// warp's six consecutive rows are adjacent in lval: ONE copy for all of them (lane 1 of the
+		// warp) unless the span is longer than the staged area (rows whose run is not their whole
+		// lower part), in which case lane 1 of every group copies its own run
 		const int uidx = (r == 2) ? u0.x : (r == 3) ? u0.y : u0.z;
+		const int lfirst = __reduce_min_sync(0xffffffffu, nk > 0 ? m0.y : 0x7fffffff);
+		const int llast = __reduce_max_sync(0xffffffffu, nk > 0 ? m0.y + nk : 0);
+		const bool lspan = (llast - lfirst) <= GPW*3;
+		unsigned loff;                                        // byte offset of this group's L run in the L area
+		{
+			const size_t s0 = (size_t)(lval + (size_t)(lspan ? lfirst : m0.y)*BS2);
+			loff = lspan ? (unsigned)((size_t)(nk > 0 ? m0.y - lfirst : 0)*BS2*8 + (s0 & 15))
+			             : (unsigned)(g*RUN_BYTES + (s0 & 15));
+		}
 		{
 			unsigned bytes = 0, dstoff = 0;
 			size_t a = 0;
-			if(active) {
+			bool to_l_area = false;
+			if(lspan && lane == 1 && llast > lfirst) {
+				a = (size_t)(lval + (size_t)lfirst*BS2); to_l_area = true;
+				bytes = ((unsigned)((llast - lfirst)*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
+			}
+			else if(active) {
 				if(r == 0) { a = (size_t)(avals + (size_t)m0.x*BS2); bytes = A_BYTES; }
-				else if(r == 1 && nk > 0) {
-					a = (size_t)(lval + (size_t)m0.y*BS2); dstoff = A_BYTES;
+				else if(!lspan && r == 1 && nk > 0) {
+					a = (size_t)(lval + (size_t)m0.y*BS2); to_l_area = true; dstoff = g*RUN_BYTES;
 					bytes = ((unsigned)(nk*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
 				}
 				else if(URUN && r == 2 && nk > 0) {
-					a = (size_t)(ut + (size_t)u0.x*BS2); dstoff = A_BYTES + RUN_BYTES;
+					a = (size_t)(ut + (size_t)u0.x*BS2); dstoff = A_BYTES;
 					bytes = ((unsigned)(nk*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
 				}
 				else if(!URUN && r >= 2 && r - 2 < nk) {
-					a = (size_t)(ut + (size_t)uidx*BS2); dstoff = A_BYTES + RUN_BYTES + (r - 2)*208;
+					a = (size_t)(ut + (size_t)uidx*BS2); dstoff = A_BYTES + (r - 2)*208;
 					bytes = 208;
 				}
 			}
 			const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
 			if(lane == 0) mbar_expect_tx(&bars[w], total);
 			if(bytes)
-				bulk_g2s(wsm + (size_t)g*GROUP_BYTES + dstoff, (const void*)(a & ~(size_t)15), bytes, &bars[w]);
+				bulk_g2s(to_l_area ? wsm + L_AREA + dstoff : wsm + (size_t)g*GROUP_BYTES + dstoff,
+				         (const void*)(a & ~(size_t)15), bytes, &bars[w]);
 		}
 		mbar_wait(&bars[w], (unsigned)(it & 1));
 
@@ -653,7 +673,7 @@ block5_upper_staged_kernel(const int nrows, const int4 *__restrict__ dmeta,
 				for(int c = 0; c < BS; c++) sum[c] *= sr*__ldg(scale + (size_t)row*BS + c);
 			}
 		}
-		const double *sl = reinterpret_cast<const double*>(gs + A_BYTES) + ((((size_t)(lval + (size_t)m0.y*BS2)) & 15) >> 3);
+		const double *sl = reinterpret_cast<const double*>(wsm + L_AREA + loff);
 		const int nkmax = __reduce_max_sync(0xffffffffu, nk);
 		for(int k = 0; k < nkmax; k++) {
 			double lr[BS], ur[BS];
@@ -661,11 +681,11 @@ block5_upper_staged_kernel(const int nrows, const int4 *__restrict__ dmeta,
 			for(int c = 0; c < BS; c++) { lr[c] = 0; ur[c] = 0; }
 			if(k < nk) {
 				const double *su;
-				if(URUN) su = reinterpret_cast<const double*>(gs + A_BYTES + RUN_BYTES)
+				if(URUN) su = reinterpret_cast<const double*>(gs + A_BYTES)
 					+ ((((size_t)(ut + (size_t)u0.x*BS2)) & 15) >> 3) + k*BS2;
 				else {
 					const int uk = (k == 0) ? u0.x : (k == 1) ? u0.y : u0.z;
-					su = reinterpret_cast<const double*>(gs + A_BYTES + RUN_BYTES + k*208)
+					su = reinterpret_cast<const double*>(gs + A_BYTES + k*208)
 						+ ((((size_t)(ut + (size_t)uk*BS2)) & 15) >> 3);
 				}
 #pragma unroll
@@ -697,8 +717,9 @@ block5_lower_staged_kernel(const int nrows, const int4 *__restrict__ rmeta,
                            double *lval)
 {
 	constexpr int BS = 5, GPW = 6, BS2 = 25;
-	constexpr int RUN_BYTES = 624, GROUP_BYTES = RUN_BYTES + 3*208;                         // 1248
-	constexpr int STAGE_BYTES = GPW*GROUP_BYTES;                                            // 7488
+	// per warp: six runs of A blocks, then three areas (one per entry position e) of six U_jj^-1 blocks
+	constexpr int RUN_BYTES = 624, D_AREA = GPW*208;                                        // 624, 1248
+	constexpr int STAGE_BYTES = GPW*RUN_BYTES + 3*D_AREA;                                   // 7488
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ __align__(8) unsigned long long bars[4];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -721,40 +742,61 @@ block5_lower_staged_kernel(const int nrows, const int4 *__restrict__ rmeta,
 		const int4 m2 = getmeta(t + 2*stride), c2 = getcols(t + 2*stride);
 		const int nl = m0.z;
 		const int row = (int)t;
-		// lane 0 of every group copies the run of A blocks, lanes 1..3 the inverses U_jj^-1
+		// lane 0 of every group copies the run of A blocks, lanes 1..3 the inverses U_jj^-1 of its
+		// entries - unless the e-th columns of the warp's six rows are consecutive (structured
+		// grids: rows i..i+5 read columns j..j+5), then lane e+1 of the warp copies all six at once
 		const int col = (r == 1) ? c0.x : (r == 2) ? c0.y : c0.z;
+		bool merged[3];
+		int colbase[3];
+#pragma unroll
+		for(int e = 0; e < 3; e++) {
+			const int ce = (e == 0) ? c0.x : (e == 1) ? c0.y : c0.z;
+			colbase[e] = __shfl_sync(0xffffffffu, ce, 0);
+			merged[e] = __all_sync(0xffffffffu, !lanevalid || (t < nrows && nl > e && ce == colbase[e] + g));
+		}
 		{
 			unsigned bytes = 0, dstoff = 0;
 			size_t a = 0;
-			if(nl > 0) {
+			// (selects, not merged[lane-1]: a lane-indexed array would live in local memory)
+			const bool my_merged = (r == 1) ? merged[0] : (r == 2) ? merged[1] : merged[2];
+			const int my_base = (r == 1) ? colbase[0] : (r == 2) ? colbase[1] : colbase[2];
+			if(lane >= 1 && lane <= 3 && my_merged) {
+				const int e = lane - 1;
+				a = (size_t)(dinv + (size_t)my_base*BS2); dstoff = GPW*RUN_BYTES + e*D_AREA;
+				bytes = ((unsigned)(GPW*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
+			}
+			else if(nl > 0) {
 				if(r == 0) {
-					a = (size_t)(avals + (size_t)m0.x*BS2);
+					a = (size_t)(avals + (size_t)m0.x*BS2); dstoff = g*RUN_BYTES;
 					bytes = ((unsigned)(nl*BS2*8) + (unsigned)(a & 15) + 15u) & ~15u;
 				}
-				else if(r >= 1 && r - 1 < nl) {
-					a = (size_t)(dinv + (size_t)col*BS2); dstoff = RUN_BYTES + (r - 1)*208;
+				else if(r >= 1 && r <= 3 && r - 1 < nl && !my_merged) {
+					a = (size_t)(dinv + (size_t)col*BS2); dstoff = GPW*RUN_BYTES + (r - 1)*D_AREA + g*208;
 					bytes = 208;
 				}
 			}
 			const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
 			if(lane == 0) mbar_expect_tx(&bars[w], total);
-			if(bytes)
-				bulk_g2s(wsm + (size_t)g*GROUP_BYTES + dstoff, (const void*)(a & ~(size_t)15), bytes, &bars[w]);
+			if(bytes) bulk_g2s(wsm + dstoff, (const void*)(a & ~(size_t)15), bytes, &bars[w]);
 		}
 		mbar_wait(&bars[w], (unsigned)(it & 1));
 
-		const unsigned char *gs = wsm + (size_t)g*GROUP_BYTES;
-		const double *sa = reinterpret_cast<const double*>(gs) + ((((size_t)(avals + (size_t)m0.x*BS2)) & 15) >> 3);
+		const double *sa = reinterpret_cast<const double*>(wsm + (size_t)g*RUN_BYTES)
+			+ ((((size_t)(avals + (size_t)m0.x*BS2)) & 15) >> 3);
 		const int nlmax = __reduce_max_sync(0xffffffffu, nl);
-		for(int e = 0; e < nlmax; e++) {
+#pragma unroll
+		for(int e = 0; e < 3; e++) {
+			if(e >= nlmax) break;
 			const bool has = e < nl;
 			const int ce = (e == 0) ? c0.x : (e == 1) ? c0.y : c0.z;
 			double s[BS], drow[BS];
 #pragma unroll
 			for(int c = 0; c < BS; c++) { s[c] = 0; drow[c] = 0; }
 			if(has) {
-				const double *sd = reinterpret_cast<const double*>(gs + RUN_BYTES + e*208)
-					+ ((((size_t)(dinv + (size_t)ce*BS2)) & 15) >> 3);
+				const unsigned char *da = wsm + GPW*RUN_BYTES + e*D_AREA;
+				const double *sd = merged[e]
+					? reinterpret_cast<const double*>(da + (((size_t)(dinv + (size_t)colbase[e]*BS2)) & 15)) + g*BS2
+					: reinterpret_cast<const double*>(da + g*208 + (((size_t)(dinv + (size_t)ce*BS2)) & 15));
 #pragma unroll
 				for(int c = 0; c < BS; c++) { s[c] = sa[e*BS2 + c*BS + r]; drow[c] = sd[c*BS + r]; }
 				if(SCALE) {

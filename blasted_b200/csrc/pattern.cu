@@ -434,6 +434,19 @@ void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 	pl.built = true;
 }
 
+void part_max_lengths(const Mat& A, int out[2], cudaStream_t st)
+{
+	out[0] = out[1] = 0;
+	if(A.nbrows == 0) return;
+	DevBuf<int> d_ml;
+	d_ml.alloc(2);
+	B200_CUDA(cudaMemsetAsync(d_ml, 0, 2*sizeof(int), st));
+	part_max_len_kernel<<<std::min(div_up(A.nbrows, 256), 148*8), 256, 0, st>>>(A.nbrows, A.browptr, A.diagind, d_ml);
+	B200_LAUNCHED();
+	B200_CUDA(cudaMemcpyAsync(out, d_ml.p, 2*sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+}
+
 // ------------------------------------------------------------------ pattern statistics
 
 __global__ void __launch_bounds__(256)
@@ -497,15 +510,27 @@ __global__ void gather_kernel(const long long n, const int *__restrict__ idx,
 	if(t < n) out[t] = in[idx[t]];
 }
 
-void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
-                         cudaStream_t st)
+__global__ void gather_blocks_kernel(const long long n, const int bs2, const int *__restrict__ idx,
+                                     const double *__restrict__ in, double *__restrict__ out)
 {
+	const long long e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(e >= n*bs2) return;
+	const long long t = e / bs2;
+	out[e] = in[(size_t)idx[t]*bs2 + (e - t*bs2)];
+}
+
+void gather_split_values(const IluPattern& pl, const double *vals, double *lval, double *uval,
+                         cudaStream_t st, int bs)
+{
+	const int bs2 = bs*bs;
 	if(pl.nlower > 0) {
-		gather_kernel<<<div_up(pl.nlower, 256), 256, 0, st>>>(pl.nlower, pl.lentry, vals, lval);
+		if(bs == 1) gather_kernel<<<div_up(pl.nlower, 256), 256, 0, st>>>(pl.nlower, pl.lentry, vals, lval);
+		else gather_blocks_kernel<<<div_up(pl.nlower*bs2, 256), 256, 0, st>>>(pl.nlower, bs2, pl.lentry, vals, lval);
 		B200_LAUNCHED();
 	}
 	if(pl.nstrict > 0) {
-		gather_kernel<<<div_up(pl.nstrict, 256), 256, 0, st>>>(pl.nstrict, pl.uentry, vals, uval);
+		if(bs == 1) gather_kernel<<<div_up(pl.nstrict, 256), 256, 0, st>>>(pl.nstrict, pl.uentry, vals, uval);
+		else gather_blocks_kernel<<<div_up(pl.nstrict*bs2, 256), 256, 0, st>>>(pl.nstrict, bs2, pl.uentry, vals, uval);
 		B200_LAUNCHED();
 	}
 }

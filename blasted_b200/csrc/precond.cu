@@ -58,6 +58,11 @@ void prec_compute(Prec& P, double precinfo[6])
 		if(!P.dinv.p) P.dinv.alloc((size_t)A.nbrows*A.bs*A.bs);
 		launch_invert_diag_blocks(A, A.vals, A.diagind, P.dinv, true, st);
 		if(first) {
+			if(A.bs > 1) {
+				int ml[2];
+				part_max_lengths(A, ml, st);
+				P.a_max_lower = ml[0]; P.a_max_upper = ml[1];
+			}
 			// ytemp allocated and zeroed once: solverops_sgs.cpp:36-43, solverops_levels_sgs.cpp:37-41
 			P.ytemp.alloc(A.dim());
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, A.dim()*sizeof(double), st));
@@ -69,8 +74,17 @@ void prec_compute(Prec& P, double precinfo[6])
 				P.sf.lval.alloc(std::max<long long>(P.pl.nlower, 1));
 				P.sf.uval.alloc(std::max<long long>(P.pl.nstrict, 1));
 			}
+			// block async SGS (bs 4, 5): the same - the forward sweep streams the L parts, the backward
+			// sweep the strict U parts, each a contiguous array (C3: 0.83 -> ~1.0 of peak per sweep);
+			// the copy is refreshed at every compute() (one pass over A)
+			if(type == B200_SGS && (A.bs == 4 || A.bs == 5)) {
+				build_split_csr(A, P.pl, st);
+				const size_t b2 = (size_t)A.bs*A.bs;
+				P.sf.lval.alloc(std::max<size_t>((size_t)P.pl.nlower*b2, 1));
+				P.sf.uval.alloc(std::max<size_t>((size_t)P.pl.nstrict*b2, 1));
+			}
 		}
-		if(P.pl.split_built) gather_split_values(P.pl, A.vals, P.sf.lval, P.sf.uval, st);
+		if(P.pl.split_built) gather_split_values(P.pl, A.vals, P.sf.lval, P.sf.uval, st, A.bs);
 	}
 	else if(P.is_ilu) {
 		const bool scalar = (A.bs == 1);       // scalar factors live in split form (P.sf), see scalar_ilu.cu
@@ -394,7 +408,11 @@ void prec_apply(Prec& P, const double *r, double *z)
 			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
 		TriArgs a; a.vals = A.vals; a.dinv = P.dinv; a.row_begin = 0; a.row_end = A.nbrows;
 		a.rhs = r; a.x = P.ytemp; a.descending = false;
-		const bool split = P.pl.split_built;
+		a.max_part_len = P.a_max_lower;
+		const bool split = P.pl.split_built && A.bs == 1;
+		if(P.pl.split_built && A.bs > 1) {        // block sweeps over the split copy of A
+			a.vals = P.sf.lval; a.part_ptr = P.pl.lptr; a.part_col = P.pl.lcol;
+		}
 		StreamArgs sa;
 		if(split) {
 			sa.ptr = P.pl.lptr; sa.col = P.pl.lcol; sa.val = P.sf.lval; sa.x = P.ytemp; sa.out = P.ytemp;
@@ -411,6 +429,10 @@ void prec_apply(Prec& P, const double *r, double *z)
 		else if(ai == B200_INIT_A_ZERO)
 			B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
 		a.rhs = P.ytemp; a.x = z; a.descending = true;
+		a.max_part_len = P.a_max_upper;
+		if(P.pl.split_built && A.bs > 1) {
+			a.vals = P.sf.uval; a.part_ptr = P.pl.uptr; a.part_col = P.pl.ucol;
+		}
 		if(split) {
 			sa = StreamArgs();
 			sa.ptr = P.pl.uptr; sa.col = P.pl.ucol; sa.val = P.sf.uval; sa.x = z; sa.out = z;
@@ -447,6 +469,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 		TriArgs aL = a, aU = a;
 		aL.vals = P.sf.lval; aL.part_ptr = P.pl.lptr; aL.part_col = P.pl.lcol;
 		aU.vals = P.sf.uval; aU.part_ptr = P.pl.uptr; aU.part_col = P.pl.ucol;
+		aL.max_part_len = P.pl.max_lower_len; aU.max_part_len = P.pl.max_upper_len;
 		if(scalar) aU.part_diag = P.sf.udiag;
 		const bool stream = scalar && stream_supported(A.max_row_len);
 		if(levelled) {
