@@ -11,6 +11,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size"]
 CLASS = {"block_ilu0_lower": "factor_lower", "block_ilu0_upper": "factor_upper",
+         "block5_lower_staged": "factor_lower", "block5_upper_staged": "factor_upper",
+         "tri5_staged_kernel<0": "tri_lower", "tri5_staged_kernel<1": "tri_upper",
          "tri_block_kernel<4, 0": "tri_lower", "tri_block_kernel<4, 1": "tri_upper",
          "tri_block_pipe_kernel<4, 0": "tri_lower", "tri_block_pipe_kernel<4, 1": "tri_upper",
          "tri_block_kernel<5, 0": "tri_lower", "tri_block_kernel<5, 1": "tri_upper",
