@@ -322,8 +322,7 @@ def run_b200(args):
     vals_np, r_np, z_np = vals_pin.numpy(), r_pin.numpy(), z_pin.numpy()
 
     def step_e2e():
-        view.update_values(vals_np)                       # H2D of the Jacobian values
-        prec.compute()
+        prec.compute(vals_np)                             # H2D of the Jacobian values + factorisation
         prec.apply(r_np, z_np)                            # H2D r, kernels, D2H z
 
     esteps = max(1, min(args.steps, 5))

@@ -61,6 +61,7 @@ SYMBOLS = {
     "b200_mat_gemv3_host": (_i, [_vp, _d, _vp, _d, _vp, _vp]),
     "b200_prec_create": (_i, [C.POINTER(Settings), _vp, _pp]),
     "b200_prec_compute": (_i, [_vp, _vp]),
+    "b200_prec_compute_host": (_i, [_vp, _vp, _vp]),
     "b200_prec_apply": (_i, [_vp, _vp, _vp]),
     "b200_prec_apply_host": (_i, [_vp, _vp, _vp]),
     "b200_prec_set_apply_params": (_i, [_vp, _d, _d, _d, _i, _i]),

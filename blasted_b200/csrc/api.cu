@@ -111,6 +111,51 @@ static void upload_values(Mat& A, const double *vals, bool from_host, cudaStream
 	}
 }
 
+/// Host values -> device, chunk by chunk on a copy stream of the matrix; after every chunk has
+/// landed (and has been converted to the device block layout) `per_chunk(first block, blocks)` is
+/// called to enqueue work on the chunk on the matrix's stream - so that the layout conversion and
+/// whatever the caller enqueues run BEHIND the next chunk's copy instead of after the whole upload.
+/// Returns when the host buffer has been consumed (the enqueued device work may still be running).
+template <typename F>
+static void upload_values_pipelined(Mat& A, const double *vals, F&& per_chunk)
+{
+	const long long bs2 = (long long)A.bs*A.bs;
+	if(A.nnzb == 0) return;
+	cudaStream_t st = A.stream;
+	if(!A.copy_stream) {
+		B200_CUDA(cudaStreamCreateWithFlags(&A.copy_stream, cudaStreamNonBlocking));
+		for(int i = 0; i < 2; i++) {
+			B200_CUDA(cudaEventCreateWithFlags(&A.ev_up[i], cudaEventDisableTiming));
+			B200_CUDA(cudaEventCreateWithFlags(&A.ev_free[i], cudaEventDisableTiming));
+		}
+	}
+	const bool convert = A.bs > 1 && (A.blockstorage == B200_ROWMAJOR) != device_rowmajor(A.bs);
+	const long long chunk_blocks = std::max<long long>(1, (32LL << 20)/(bs2*8));          // 32 MiB
+	const long long cb = std::min<long long>(chunk_blocks, A.nnzb);
+	if(convert) A.stage.alloc((size_t)cb*bs2*2);
+	// the copy stream starts after what is already enqueued on the matrix's stream (the previous
+	// values may still be in use there)
+	B200_CUDA(cudaEventRecord(A.ev_free[0], st));
+	B200_CUDA(cudaStreamWaitEvent(A.copy_stream, A.ev_free[0], 0));
+	int which = 0;
+	long long k = 0;
+	for(long long b0 = 0; b0 < A.nnzb; b0 += chunk_blocks, which ^= 1, k++) {
+		const long long nb = std::min<long long>(chunk_blocks, A.nnzb - b0);
+		double *dst = convert ? A.stage.p + (size_t)which*cb*bs2 : A.vals.p + b0*bs2;
+		// a staging buffer is free again once the conversion of the chunk before last has run
+		if(convert && k >= 2) B200_CUDA(cudaStreamWaitEvent(A.copy_stream, A.ev_free[which], 0));
+		B200_CUDA(cudaMemcpyAsync(dst, vals + b0*bs2, nb*bs2*sizeof(double), cudaMemcpyHostToDevice, A.copy_stream));
+		B200_CUDA(cudaEventRecord(A.ev_up[which], A.copy_stream));
+		B200_CUDA(cudaStreamWaitEvent(st, A.ev_up[which], 0));
+		if(convert) {
+			transpose_blocks(A.bs, nb, dst, A.vals.p + b0*bs2, st);
+			B200_CUDA(cudaEventRecord(A.ev_free[which], st));
+		}
+		per_chunk(b0, nb);
+	}
+	B200_CUDA(cudaStreamSynchronize(A.copy_stream));        // the host buffer has been read
+}
+
 /// Copies a device vector of block values out in the caller's block layout
 static void download_blocks(const Mat& A, long long nblocks, const double *d_src, double *h_dst,
                             cudaStream_t st)
@@ -277,7 +322,16 @@ int b200_mat_update_values_device(b200_mat *m, const double *d_vals)
 	return guarded([&] { upload_values(m->m, d_vals, false, m->m.stream); });
 }
 
-void b200_mat_destroy(b200_mat *m) { delete m; }
+void b200_mat_destroy(b200_mat *m)
+{
+	if(!m) return;
+	for(int i = 0; i < 2; i++) {
+		if(m->m.ev_up[i]) cudaEventDestroy(m->m.ev_up[i]);
+		if(m->m.ev_free[i]) cudaEventDestroy(m->m.ev_free[i]);
+	}
+	if(m->m.copy_stream) cudaStreamDestroy(m->m.copy_stream);
+	delete m;
+}
 int b200_mat_dim(const b200_mat *m) { return m->m.dim(); }
 int b200_mat_nbrows(const b200_mat *m) { return m->m.nbrows; }
 long long b200_mat_nnzb(const b200_mat *m) { return m->m.nnzb; }
@@ -482,6 +536,28 @@ int b200_prec_create(const b200_settings *s, b200_mat *m, b200_prec **out)
 int b200_prec_compute(b200_prec *p, double precinfo[6])
 {
 	return guarded([&] { prec_compute(p->p, precinfo); });
+}
+
+int b200_prec_compute_host(b200_prec *p, const double *vals, double precinfo[6])
+{
+	return guarded([&] {
+		Prec& P = p->p;
+		Mat& A = *P.A;
+		if(!vals) { prec_compute(P, precinfo); return; }
+		if(P.stream != A.stream)
+			throw Error("compute: the matrix and the preconditioner are on different streams");
+		if(prec_init_is_chunkable(P)) {
+			// values, layout conversion and the initial guess of the factor travel chunk by chunk:
+			// only the last chunk's conversion + initialisation are not hidden behind a copy
+			upload_values_pipelined(A, vals, [&](long long b0, long long nb) {
+				launch_ilu0_init_range(A, P.pl, P.sf, b0, b0 + nb, A.stream);
+			});
+			prec_compute(P, precinfo, true);
+		} else {
+			upload_values_pipelined(A, vals, [](long long, long long) {});
+			prec_compute(P, precinfo);
+		}
+	});
 }
 
 int b200_prec_apply(b200_prec *p, const double *d_r, double *d_z)

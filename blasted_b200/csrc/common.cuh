@@ -140,6 +140,8 @@ struct Mat {
 	cudaStream_t stream = 0;
 	mutable DevBuf<double> hx, hy, hz;    ///< staging for the *_host entry points
 	DevBuf<double> stage;                 ///< fixed staging buffer for layout-converting uploads
+	cudaStream_t copy_stream = nullptr;   ///< host uploads of the values run beside the conversion / initialisation
+	cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
 	mutable KrylovStore krylov_ws;        ///< Krylov basis storage, kept between solves (grow-only)
 
 	int dim() const { return nbrows*bs; }
@@ -265,6 +267,9 @@ void block_factor_alloc(const Mat& A, const IluPattern& pl, ScalarFactor& F);
 /// Writes the initial guess (INIT_F_ORIGINAL / _SGS / _ZERO) into the split arrays.
 void launch_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
                       ScalarFactor& F, cudaStream_t st);
+/// INIT_F_ORIGINAL (unscaled) on the block entries [e0, e1) only
+void launch_ilu0_init_range(const Mat& A, const IluPattern& pl, ScalarFactor& F, long long e0,
+                            long long e1, cudaStream_t st);
 /// One asynchronous sweep (lower launch, then upper launch).  If d_changed is non-null it is set to
 /// 1 when any entry's value changed bitwise (used to iterate to the exact fixed point).
 /// `all_upper`: also recompute the upper entries without products (needed once when the initial
@@ -402,7 +407,11 @@ struct b200_mat { b200::Mat m; };
 struct b200_prec { b200::Prec p; };
 namespace b200 {
 
-void prec_compute(Prec& P, double precinfo[6]);
+/// init_done: the initial guess (INIT_F_ORIGINAL) has already been written for the current values
+/// (chunk-wise, by b200_prec_compute_host)
+void prec_compute(Prec& P, double precinfo[6], bool init_done = false);
+/// whether prec_compute's initialisation can run chunk by chunk behind an upload of the values
+bool prec_init_is_chunkable(const Prec& P);
 void prec_apply(Prec& P, const double *d_r, double *d_z);
 void prec_apply_relax(Prec& P, const double *d_b, double *d_x, int maxits);
 /// Synchronises the handle's stream and raises (once) if a one-launch exact substitution recorded a

@@ -88,7 +88,7 @@ enum { MODE_INIT_SGS = 2, MODE_INIT_ORIG = 3 };
 /// A group of BS lanes per stored block; lane r holds row r of the block.
 template <int BS, bool SCALE, int MODE>
 __global__ void __launch_bounds__(256)
-block_split_init_kernel(const long long nnzb, const int *__restrict__ browptr,
+block_split_init_kernel(const long long entry0, const long long nnzb, const int *__restrict__ browptr,
                         const int *__restrict__ bcolind, const int *__restrict__ browind,
                         const int *__restrict__ diagind, const int *__restrict__ lptr,
                         const int *__restrict__ uptr, const int *__restrict__ utpos,
@@ -101,7 +101,7 @@ block_split_init_kernel(const long long nnzb, const int *__restrict__ browptr,
 	const int lane = threadIdx.x & 31;
 	const long long warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
 	const int g = lane / BS, r = lane - g*BS;
-	const long long entry = warp*GPW + g;
+	const long long entry = entry0 + warp*GPW + g;           // entries [entry0, nnzb)
 	if(g >= GPW || entry >= nnzb) return;
 	const int row = __ldg(browind + entry), col = __ldg(bcolind + entry);
 	const int dg = __ldg(diagind + row);
@@ -1053,12 +1053,14 @@ void block_factor_alloc(const Mat& A, const IluPattern& pl, ScalarFactor& F)
 
 template <int BS>
 static void launch_block_init(const Mat& A, const IluPattern& pl, const double *scale, int fact_init,
-                              ScalarFactor& F, cudaStream_t st)
+                              ScalarFactor& F, cudaStream_t st, long long e0 = 0, long long e1 = -1)
 {
 	constexpr int GPW = 32/BS;
-	const long long nwarps = (A.nnzb + GPW - 1)/GPW;
+	if(e1 < 0) e1 = A.nnzb;
+	if(e1 <= e0) return;
+	const long long nwarps = (e1 - e0 + GPW - 1)/GPW;
 	const int grid = div_up(nwarps*32, 256);
-#define B200_INIT(SC, MODE) block_split_init_kernel<BS,SC,MODE><<<grid,256,0,st>>>(A.nnzb, A.browptr, \
+#define B200_INIT(SC, MODE) block_split_init_kernel<BS,SC,MODE><<<grid,256,0,st>>>(e0, e1, A.browptr, \
 		A.bcolind, A.browind, A.diagind, pl.lptr, pl.uptr, pl.utpos, A.vals, scale, F.lval.p,         \
 		F.udiag.p, F.uval.p, F.ut.p)
 	if(fact_init == B200_INIT_F_SGS) { if(scale) B200_INIT(true, MODE_INIT_SGS); else B200_INIT(false, MODE_INIT_SGS); }
@@ -1084,6 +1086,19 @@ void launch_ilu0_init(const Mat& A, const IluPattern& pl, const double *scale, i
 	switch(A.bs) {
 	case 4: launch_block_init<4>(A, pl, scale, fact_init, F, st); break;
 	case 5: launch_block_init<5>(A, pl, scale, fact_init, F, st); break;
+	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
+	}
+}
+
+void launch_ilu0_init_range(const Mat& A, const IluPattern& pl, ScalarFactor& F, long long e0,
+                            long long e1, cudaStream_t st)
+{
+	// INIT_F_ORIGINAL without scaling reads nothing but the entry itself: it can run on the block
+	// entries [e0, e1) alone (chunk-wise, behind the upload of the next chunk)
+	ProfScope ps(KC_FACTOR_INIT, st);
+	switch(A.bs) {
+	case 4: launch_block_init<4>(A, pl, nullptr, B200_INIT_F_ORIGINAL, F, st, e0, e1); break;
+	case 5: launch_block_init<5>(A, pl, nullptr, B200_INIT_F_ORIGINAL, F, st, e0, e1); break;
 	default: throw Error("ILU0: unsupported block size " + std::to_string(A.bs));
 	}
 }

@@ -37,7 +37,13 @@ static void ensure_events(Prec& P)
 
 static bool exact_in_one_launch(Prec& P);
 
-void prec_compute(Prec& P, double precinfo[6])
+bool prec_init_is_chunkable(const Prec& P)
+{
+	return P.computed && P.is_ilu && P.A->bs > 1 && P.pl.built && !P.s.scale &&
+	       P.s.fact_inittype == B200_INIT_F_ORIGINAL;
+}
+
+void prec_compute(Prec& P, double precinfo[6], bool init_done)
 {
 	Mat& A = *P.A;
 	cudaStream_t st = P.stream;
@@ -123,7 +129,7 @@ void prec_compute(Prec& P, double precinfo[6])
 		else {
 			// (inverting the initial diagonal blocks inside the init launch was measured slower: every
 			// warp then runs the elimination, 322 us against 189 + 74 us for the two passes on C2)
-			launch_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
+			if(!init_done) launch_ilu0_init(A, P.pl, scale, P.s.fact_inittype, P.sf, st);
 			launch_invert_diag_blocks(A, P.sf.udiag, nullptr, dinv, true, st);
 		}
 

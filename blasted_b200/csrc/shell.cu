@@ -261,9 +261,9 @@ int b200_shell_setup(b200_shell_node *node, int bs, int nbrows, const int *ia, c
 			throw std::runtime_error("shell: the local matrix changed size between setups");
 		Stopwatch sw;
 		// updatePreconditioner, :314-327: PETSc has rewritten `a` in place; same pattern
-		if(!created && a) need(b200_mat_update_values_host(node->bmat, a));   // (creation uploaded them)
+		// (creation uploaded the values; later set-ups upload and factorise in one pipelined call)
 		double info[6] = {0, 0, 0, 0, 0, 0};
-		need(b200_prec_compute(node->bprec, info));
+		need(b200_prec_compute_host(node->bprec, (!created && a) ? a : nullptr, info));
 		// compute() only enqueues; the set-up time of the reference (blasted_petsc.cpp:321-326) is
 		// that of the finished factorisation, so wait for it before the stopwatch is read
 		{ double ms = 0; need(b200_prec_last_times(node->bprec, &ms, nullptr)); }

@@ -276,9 +276,16 @@ class Preconditioner:
         lib.b200_prec_set_apply_params(self._h, float(rtol), float(atol), float(dtol), int(ctol),
                                        int(maxits))
 
-    def compute(self) -> PrecInfo:
+    def compute(self, vals=None) -> PrecInfo:
+        """Preconditioner::compute().  With `vals` (host array of new matrix values, same pattern):
+        the values are uploaded chunk by chunk with the layout conversion and the initial guess of
+        the factor behind the copies (b200_prec_compute_host)."""
         info = np.zeros(6)
-        check(lib.b200_prec_compute(self._h, info.ctypes.data_as(C.c_void_p)))
+        if vals is None:
+            check(lib.b200_prec_compute(self._h, info.ctypes.data_as(C.c_void_p)))
+        else:
+            _, vp = _host(vals)
+            check(lib.b200_prec_compute_host(self._h, vp, info.ctypes.data_as(C.c_void_p)))
         return PrecInfo(info)
 
     def apply(self, r, z=None):

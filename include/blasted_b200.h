@@ -176,6 +176,14 @@ int b200_prec_create(const b200_settings *settings, b200_mat *m, b200_prec **out
  *  the ILU position lists / level schedule on the device (src/solverops_ilu0.cpp:190-202,358-368).
  *  precinfo may be NULL; layout = PrecInfo::f_info (include/preconditioner_diagnostics.hpp:14-58). */
 int b200_prec_compute(b200_prec *p, double precinfo[6]);
+/** The update a Newton / time-stepping loop performs between solves, in one call: new values of
+ *  the matrix from host memory (same pattern - PETSc rewrites `a` in place between compute()
+ *  calls, include/solverops_ilu0.hpp:53-56, src/blasted_petsc.cpp:314-327) followed by compute().
+ *  The values travel in chunks on a copy stream; the layout conversion and, where it depends on
+ *  nothing but the entry itself (ILU0 types on blocks, INIT_F_ORIGINAL, no scaling), the initial
+ *  guess of the factor run behind the next chunk's copy.  Returns when `vals` has been read;
+ *  the factorisation itself is only enqueued.  vals == NULL: plain b200_prec_compute. */
+int b200_prec_compute_host(b200_prec *p, const double *vals, double precinfo[6]);
 /** Preconditioner::apply(r, z) : z = M^-1 r. */
 int b200_prec_apply(b200_prec *p, const double *d_r, double *d_z);
 int b200_prec_apply_host(b200_prec *p, const double *r, double *z);

@@ -279,3 +279,31 @@ def test_block_factor_on_a_general_pattern(bs, scaled):
     a = make(m, "sfilu0", scale=scaled, nbuildsweeps=1, napplysweeps=80)
     a.compute()
     assert relerr(a.apply(r), q.apply(r)) < 1e-11
+
+
+@pytest.mark.parametrize("key", ["2dcyl1_bsr4", "2dcyl1_bsr4r", "synth_bsr5", "2dcyl1_csr"])
+def test_compute_with_new_host_values_equals_update_then_compute(key):
+    """b200_prec_compute_host (values uploaded chunk by chunk, layout conversion and initial guess
+    behind the copies) gives bit for bit what update_values + compute gives - on exact types, so
+    that the comparison is deterministic."""
+    m = case(key)
+    view = bb.SRMatrixView(m)
+    s = bb.AsyncSolverSettings(prectype=SOLVER_TYPES["sfilu0"], bs=m.bs, blockstorage=1 if m.rowmajor else 0)
+    p = bb.SRFactory().create_preconditioner(view, s)
+    p.compute()
+    rng = np.random.default_rng(SEED + 11)
+    newvals = m.vals*(1.0 + 0.01*rng.standard_normal(m.vals.shape))
+    p.compute(newvals)
+    got = p.factor()
+    view2 = bb.SRMatrixView(m)
+    q = bb.SRFactory().create_preconditioner(view2, s)
+    q.compute()
+    view2.update_values(newvals)
+    q.compute()
+    assert np.array_equal(got, q.factor())
+    # and the asynchronous type after the pipelined upload converges to the same factor
+    a = bb.SRFactory().create_preconditioner(view, bb.AsyncSolverSettings(
+        prectype=SOLVER_TYPES["ilu0"], bs=m.bs, blockstorage=1 if m.rowmajor else 0, nbuildsweeps=60))
+    a.compute()
+    a.compute(newvals)
+    assert relerr(a.factor(), got) < 1e-11
