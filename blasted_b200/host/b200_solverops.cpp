@@ -56,10 +56,11 @@ bool B200Preconditioner::relaxationAvailable() const
 
 PrecInfo B200Preconditioner::compute()
 {
-	check_runtime(b200_mat_update_values_host(dmat, mat.vals));
+	// the caller (PETSc) has rewritten the wrapped values in place: upload and factorise in one
+	// pipelined call (layout conversion and initial guess behind the copies)
 	PrecInfo info;
 	double f[6];
-	check_runtime(b200_prec_compute(dprec, f));
+	check_runtime(b200_prec_compute_host(dprec, mat.vals, f));
 	for(int i = 0; i < 6; i++) info.f_info[i] = f[i];
 	return info;
 }
