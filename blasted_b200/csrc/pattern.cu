@@ -19,6 +19,8 @@
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <cuda/functional>
 
 namespace b200 {
 
@@ -233,6 +235,7 @@ __global__ void upper_dest_transposed_kernel(const long long n, int4 *__restrict
 }
 
 __global__ void iota_kernel(int n, int *out);
+__global__ void fill_int_kernel(int n, int v, int *out);
 
 void build_ilu_pattern(const Mat& A, IluPattern& pl, cudaStream_t st)
 {
@@ -611,50 +614,45 @@ __global__ void symmetry_check_kernel(const long long nnzb, const int *__restric
 
 // ------------------------------------------------------------------ contiguous levels
 
-/// One CTA walks the rows in order.  d(r) = largest column below r in row r (-1 if none) is staged
-/// in shared memory by all threads; warp 0 then finds the level boundaries with ballots.
-__global__ void __launch_bounds__(1024)
-contiguous_levels_kernel(const int nbrows, const int *__restrict__ browptr,
-                         const int *__restrict__ bcolind, const int *__restrict__ diagind,
-                         int *__restrict__ levels, int *__restrict__ nlevels_out)
-{
-	constexpr int CHUNK = 8192;
-	__shared__ int d[CHUNK];
-	__shared__ int s_level_start, s_count;
-	if(threadIdx.x == 0) { s_level_start = 0; s_count = 1; levels[0] = 0; }
-	__syncthreads();
+// computeLevels (src/levelschedule.cpp:12-71) reduces, for sorted columns and a structurally
+// symmetric pattern, to: level k starts at s_k, s_0 = 0, s_{k+1} = min{ r > s_k : d(r) >= s_k } with
+// d(r) = the largest column below r in row r (-1 if none).  d(r) >= s implies r > s, hence
+//     next(s) = min{ r : d(r) >= s } = min over v >= s of m[v],   m[v] = min{ r : d(r) = v },
+// a scatter-min followed by a suffix-min SCAN, and the level starts are the orbit of 0 under next,
+// marked by pointer doubling (round k marks what is 2^k steps behind everything marked so far).
+// All of it runs on the whole grid in O(n log n) work; the reference (and round 1: one CTA) walks
+// the rows one after the other.  Bit-identical output (tests/test_gpu_setup.py).
 
-	for(int base = 0; base < nbrows; base += CHUNK) {
-		const int len = min(CHUNK, nbrows - base);
-		for(int t = threadIdx.x; t < len; t += blockDim.x) {
-			const int r = base + t;
-			const int dp = diagind[r];
-			d[t] = (dp > browptr[r]) ? bcolind[dp-1] : -1;
-		}
-		__syncthreads();
-		if(threadIdx.x < 32) {
-			const int lane = threadIdx.x;
-			int s = s_level_start, cnt = s_count;
-			int t = 0;
-			while(t < len) {
-				const int tt = t + lane;
-				const bool brk = (tt < len) && (d[tt] >= s) && (base + tt > s);
-				const unsigned m = __ballot_sync(0xffffffffu, brk);
-				if(m == 0) { t += 32; continue; }
-				const int f = __ffs(m) - 1;
-				s = base + t + f;                  // row s starts a new level
-				if(lane == 0) levels[cnt] = s;
-				cnt++;
-				t = t + f + 1;
-			}
-			if(lane == 0) { s_level_start = s; s_count = cnt; }
-		}
-		__syncthreads();
-	}
-	if(threadIdx.x == 0) {
-		levels[s_count] = nbrows;
-		*nlevels_out = s_count;            // number of levels; entries written = s_count+1
-	}
+/// mr[n-1-d(r)] = min(mr[..], r): m mirrored, so that an inclusive min-scan gives the suffix minima
+__global__ void __launch_bounds__(256)
+level_scatter_min_kernel(const int n, const int *__restrict__ browptr, const int *__restrict__ bcolind,
+                         const int *__restrict__ diagind, int *__restrict__ mr)
+{
+	const int r = blockIdx.x*blockDim.x + threadIdx.x;
+	if(r >= n) return;
+	const int dp = diagind[r];
+	if(dp > browptr[r]) atomicMin(mr + (n - 1 - bcolind[dp-1]), r);
+}
+
+/// J[s] = next(s) = sr[n-1-s] for s < n, J[n] = n; flag = {0}
+__global__ void __launch_bounds__(256)
+level_next_kernel(const int n, const int *__restrict__ sr, int *__restrict__ J, char *__restrict__ flag)
+{
+	const int s = blockIdx.x*blockDim.x + threadIdx.x;
+	if(s > n) return;
+	J[s] = (s < n) ? sr[n - 1 - s] : n;
+	flag[s] = (s == 0) ? 1 : 0;
+}
+
+/// one doubling round: mark J[u] for every marked u, J2 = J o J
+__global__ void __launch_bounds__(256)
+level_double_kernel(const int n, const int *__restrict__ J, int *__restrict__ J2, char *flag)
+{
+	const int u = blockIdx.x*blockDim.x + threadIdx.x;
+	if(u > n) return;
+	const int j = J[u];
+	if(flag[u] && j < n) flag[j] = 1;
+	J2[u] = J[j];
 }
 
 // ------------------------------------------------------------------ DAG levels
@@ -717,6 +715,12 @@ dag_levels_syncfree_kernel(const int nbrows, const int *__restrict__ browptr,
 	}
 }
 
+__global__ void fill_int_kernel(int n, int v, int *out)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) out[i] = v;
+}
+
 __global__ void iota_kernel(int n, int *out)
 {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -753,14 +757,43 @@ void build_levels(const Mat& A, Levels& lv, int mode, cudaStream_t st)
 		B200_CUDA(cudaStreamSynchronize(st));
 		if(bad) throw Error("Faulty dependency list!");
 
-		lv.d_level_ptr.alloc((size_t)n + 1);
-		DevBuf<int> d_nl;
-		d_nl.alloc(1);
-		contiguous_levels_kernel<<<1, 1024, 0, st>>>(n, A.browptr, A.bcolind, A.diagind,
-		                                             lv.d_level_ptr, d_nl);
-		B200_LAUNCHED();
-		B200_CUDA(cudaMemcpyAsync(&lv.nlevels, d_nl, sizeof(int), cudaMemcpyDeviceToHost, st));
-		B200_CUDA(cudaStreamSynchronize(st));
+		{
+			DevBuf<int> mr, sr, J, J2, d_nl;
+			DevBuf<char> flag;
+			mr.alloc(n); sr.alloc(n); J.alloc((size_t)n + 1); J2.alloc((size_t)n + 1); flag.alloc((size_t)n + 1);
+			d_nl.alloc(1);
+			// m[v] = n ("no row") everywhere, then the scatter-min
+			fill_int_kernel<<<div_up(n, 256), 256, 0, st>>>(n, n, mr);
+			B200_LAUNCHED();
+			level_scatter_min_kernel<<<div_up(n, 256), 256, 0, st>>>(n, A.browptr, A.bcolind, A.diagind, mr);
+			B200_LAUNCHED();
+			size_t tb = 0;
+			cub::DeviceScan::InclusiveScan(nullptr, tb, mr.p, sr.p, cuda::minimum<>{}, n, st);
+			DevBuf<char> tmp;
+			tmp.alloc(tb);
+			B200_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, mr.p, sr.p, cuda::minimum<>{}, n, st));
+			g_launches.fetch_add(1);
+			level_next_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, sr, J, flag);
+			B200_LAUNCHED();
+			int *Ja = J.p, *Jb = J2.p;
+			for(long long reach = 1; reach <= (long long)n; reach *= 2) {
+				level_double_kernel<<<div_up(n + 1, 256), 256, 0, st>>>(n, Ja, Jb, flag);
+				B200_LAUNCHED();
+				std::swap(Ja, Jb);
+			}
+			// level starts = the marked rows in ascending order, then n
+			lv.d_level_ptr.alloc((size_t)n + 1);
+			size_t tb2 = 0;
+			thrust::counting_iterator<int> ids(0);
+			cub::DeviceSelect::Flagged(nullptr, tb2, ids, flag.p, lv.d_level_ptr.p, d_nl.p, n, st);
+			DevBuf<char> tmp2;
+			tmp2.alloc(tb2);
+			B200_CUDA(cub::DeviceSelect::Flagged(tmp2.p, tb2, ids, flag.p, lv.d_level_ptr.p, d_nl.p, n, st));
+			g_launches.fetch_add(1);
+			B200_CUDA(cudaMemcpyAsync(&lv.nlevels, d_nl, sizeof(int), cudaMemcpyDeviceToHost, st));
+			B200_CUDA(cudaStreamSynchronize(st));
+			B200_CUDA(cudaMemcpyAsync(lv.d_level_ptr.p + lv.nlevels, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+		}
 		lv.level_ptr.resize(lv.nlevels + 1);
 		B200_CUDA(cudaMemcpyAsync(lv.level_ptr.data(), lv.d_level_ptr, (lv.nlevels+1)*sizeof(int),
 		                          cudaMemcpyDeviceToHost, st));

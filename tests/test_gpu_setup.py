@@ -83,6 +83,25 @@ def test_dag_levels(mk, expect):
     assert np.array_equal(ptr, np.concatenate([[0], np.cumsum(np.bincount(lv))]).astype(np.int32))
 
 
+@pytest.mark.parametrize("n,density,seed", [(1, 0.0, 0), (7, 0.0, 1), (33, 0.2, 2), (500, 0.01, 3),
+                                            (5000, 0.0008, 4), (20000, 0.0001, 5)])
+def test_contiguous_levels_random_symmetric_patterns(n, density, seed):
+    """Scatter-min + suffix-min scan + pointer doubling against the row-by-row walk of computeLevels
+    (src/levelschedule.cpp:12-71) on irregular structurally symmetric patterns (diagonal-only and
+    1x1 included: one level)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(SEED + seed)
+    a = sp.random(n, n, density=density, random_state=rng, format="csr")
+    a = (a + a.T + sp.identity(n) * (n + 1.0)).tocsr()
+    a.sort_indices()
+    m = matgen.from_scipy(a)
+    p = make(m, "level_sgs", level_mode=LEVELS_CONTIGUOUS)
+    p.compute()
+    ptr, rows = p.levels()
+    assert np.array_equal(ptr, orc().compute_levels(m))
+    assert np.array_equal(rows, np.arange(n))
+
+
 def test_nonsymmetric_pattern_rejected_for_contiguous_levels():
     import scipy.sparse as sp
     a = sp.csr_matrix(np.array([[2., 1, 0], [0, 2, 0], [0, 1, 2]]))
