@@ -39,6 +39,8 @@ SYMBOLS = {
     "b200_profile_enable": (None, [_i]),
     "b200_profile_reset": (None, []),
     "b200_profile_get": (_i, [_vp, _vp]),
+    "b200_profile_classes": (_i, []),
+    "b200_profile_get_n": (_i, [_i, _vp, _vp]),
     "b200_mat_create_host": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _pp]),
     "b200_mat_create_device": (_i, [_i, _i, _i, _vp, _vp, _vp, _pp]),
     "b200_mat_update_values_host": (_i, [_vp, _vp]),
@@ -93,6 +95,7 @@ SYMBOLS = {
     "b200_dist_mat_create": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _pp]),
     "b200_dist_mat_destroy": (None, [_vp]),
     "b200_dist_mat_apply": (_i, [_vp, _vp, _vp]),
+    "b200_dist_mat_apply_with_halo": (_i, [_vp, _vp, _vp, _vp]),
     "b200_dist_solve": (_i, [C.c_char_p, _vp, _vp, _vp, _vp, _d, _i, _i, C.POINTER(SolveInfo)]),
 }
 

@@ -256,7 +256,16 @@ int b200_profile_get(double ms[8], long long count[8])
 {
 	return guarded([&] {
 		g_prof.collect();
-		for(int i = 0; i < KC_COUNT; i++) { ms[i] = g_prof.ms[i]; count[i] = g_prof.count[i]; }
+		for(int i = 0; i < KC_BASIC; i++) { ms[i] = g_prof.ms[i]; count[i] = g_prof.count[i]; }
+	});
+}
+int b200_profile_classes(void) { return KC_COUNT; }
+int b200_profile_get_n(int n, double *ms, long long *count)
+{
+	return guarded([&] {
+		if(n < 0 || n > KC_COUNT || !ms || !count) throw Error("profile_get_n: invalid arguments");
+		g_prof.collect();
+		for(int i = 0; i < n; i++) { ms[i] = g_prof.ms[i]; count[i] = g_prof.count[i]; }
 	});
 }
 

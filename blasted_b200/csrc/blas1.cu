@@ -25,6 +25,7 @@ __global__ void axpbypcz_kernel(const long long n, const double p, double *z, co
 
 void launch_axpby(long long n, double p, double *z, double q, const double *x, cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(n == 0) return;
 	axpby_kernel<<<div_up(n,256),256,0,st>>>(n, p, z, q, x);
 	B200_LAUNCHED();
@@ -33,6 +34,7 @@ void launch_axpby(long long n, double p, double *z, double q, const double *x, c
 void launch_axpbypcz(long long n, double p, double *z, double q, const double *x, double r,
                      const double *y, cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(n == 0) return;
 	axpbypcz_kernel<<<div_up(n,256),256,0,st>>>(n, p, z, q, x, r, y);
 	B200_LAUNCHED();
@@ -137,6 +139,7 @@ multi_dot_stage2(const int nd, const int nblocks, const double *__restrict__ par
 void launch_multi_dot(long long n, int nd, const double *const *a, const double *const *b,
                       double *d_partial, double *d_out, cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(nd < 1 || nd > MAX_DOTS) throw Error("multi_dot: bad count");
 	DotPtrs p;
 	for(int d = 0; d < MAX_DOTS; d++) { p.a[d] = a[d < nd ? d : 0]; p.b[d] = b[d < nd ? d : 0]; }
@@ -241,6 +244,7 @@ update_diffnorm_kernel(const long long n, const double *__restrict__ xtemp, doub
 
 void launch_update_diffnorm(long long n, const double *xtemp, double *x, double *d_out, cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
 	if(n == 0) return;
 	const int grid = (int)std::max<long long>(1, std::min<long long>(DOT_BLOCKS, div_up(n, 256)));
@@ -250,6 +254,7 @@ void launch_update_diffnorm(long long n, const double *xtemp, double *x, double 
 
 void launch_vec_scal(long long n, double alpha, const double *in, double *out, cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(n == 0) return;
 	vec_scal_kernel<<<div_up(n,256),256,0,st>>>(n, alpha, in, out);
 	B200_LAUNCHED();
@@ -259,6 +264,7 @@ void launch_multi_axpy_scaled(long long n, int nv, const double *const *v, const
                               const double *y, double *out, const double *d_scale, cudaStream_t st,
                               double sign)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(n == 0) return;
 	if(nv > 32) throw Error("multi_axpy: too many vectors");
 	AxpyPtrs p;
@@ -270,6 +276,7 @@ void launch_multi_axpy_scaled(long long n, int nv, const double *const *v, const
 void launch_fgmres_column(int j, const double *d_dots, double *d_hcol, int hn_slot, double *d_inv_hn,
                           cudaStream_t st)
 {
+	ProfScope ps(KC_BLAS1, st);
 	fgmres_column_kernel<<<1,32,0,st>>>(j, d_dots, d_hcol, hn_slot, d_inv_hn);
 	B200_LAUNCHED();
 }
@@ -277,6 +284,7 @@ void launch_fgmres_column(int j, const double *d_dots, double *d_hcol, int hn_sl
 void launch_multi_axpy(long long n, int nv, const double *const *v, const double *d_coef, double *y,
                        cudaStream_t st, double sign)
 {
+	ProfScope ps(KC_BLAS1, st);
 	if(n == 0 || nv == 0) return;
 	if(nv > 32) throw Error("multi_axpy: too many vectors");
 	AxpyPtrs p;

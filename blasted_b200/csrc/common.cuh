@@ -53,7 +53,10 @@ extern std::atomic<long long> g_launches;
 // stream, accumulated on request.  This is what bench.py uses for the live roofline figure.
 
 enum KClass { KC_FACTOR_LOWER = 0, KC_FACTOR_UPPER, KC_FACTOR_INIT, KC_DIAG_INVERT, KC_TRI_LOWER,
-              KC_TRI_UPPER, KC_SPMV, KC_OTHER, KC_COUNT };
+              KC_TRI_UPPER, KC_SPMV, KC_OTHER,
+              // classes of the Krylov drivers and of the partitioned layer (b200_profile_get_n)
+              KC_BLAS1, KC_HALO_PACK, KC_HALO_WAIT, KC_ALLREDUCE, KC_COUNT };
+constexpr int KC_BASIC = 8;             ///< what b200_profile_get's fixed arrays hold
 
 struct Profiler {
 	bool enabled = false;
@@ -154,6 +157,12 @@ struct Mat {
 void launch_spmv(const Mat& A, const double *x, double *y, cudaStream_t st);
 void launch_gemv3(const Mat& A, double a, const double *x, double b, const double *y, double *z,
                   cudaStream_t st);
+
+/// z(rows) += a (A x)(rows) over a device list of block rows; nonempty_rows builds the list of the
+/// rows of A that hold entries (returns its length)
+void launch_gemv_add_rows(const Mat& A, int nlist, const int *d_rows, double a, const double *x,
+                          double *z, cudaStream_t st);
+int nonempty_rows(const Mat& A, DevBuf<int>& rows, cudaStream_t st);
 
 // storage.cu
 void transpose_blocks(int bs, long long nblocks, const double *in, double *out, cudaStream_t st);

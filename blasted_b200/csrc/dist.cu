@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cstring>
+#include <memory>
 
 
 namespace b200 {
@@ -96,13 +97,19 @@ struct DistMat {
 	long long nsend = 0;
 	DevBuf<int> send_idx;                       ///< local (block) rows to send, grouped by neighbour
 	DevBuf<double> send_buf, halo;
+	DevBuf<int> offd_rows;                      ///< block rows that couple to another subdomain
+	int n_offd_rows = 0;
 	cudaStream_t stream = 0;
 	// the exchange runs on its own stream so that it overlaps the diagonal-block product
 	cudaStream_t comm_stream = nullptr;
 	cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
 	void ensure_comm_stream() {
 		if(comm_stream) return;
-		B200_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+		// highest priority: the exchange kernels are tiny and must get onto the SMs while the
+		// diagonal-block product (posted first, thousands of CTAs) is still being dispatched
+		int lo = 0, hi = 0;
+		B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		B200_CUDA(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, hi));
 		B200_CUDA(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
 		B200_CUDA(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
 	}
@@ -121,6 +128,7 @@ struct DistMat {
 static bool halo_exchange(DistMat& D, const double *x)
 {
 	if(D.nsend > 0) {
+		ProfScope ps(KC_HALO_PACK, D.stream);
 		pack_kernel<<<div_up(D.nsend*D.bs, 256), 256, 0, D.stream>>>(D.nsend, D.bs, D.send_idx, x, D.send_buf);
 		B200_LAUNCHED();
 	}
@@ -153,9 +161,12 @@ static void dist_spmv(DistMat& D, double a, const double *x, double b, const dou
 	const bool inflight = halo_exchange(D, x);
 	if(plain) launch_spmv(*D.diag, x, z, D.stream);      // overlaps the exchange
 	else launch_gemv3(*D.diag, a, x, b, y, z, D.stream);
-	if(inflight) B200_CUDA(cudaStreamWaitEvent(D.stream, D.ev_halo, 0));
-	if(D.offd && D.offd->nnzb > 0)                       // z += a * A_offd * halo
-		launch_gemv3(*D.offd, plain ? 1.0 : a, D.halo, 1.0, z, z, D.stream);
+	if(inflight) {
+		ProfScope ps(KC_HALO_WAIT, D.stream);
+		B200_CUDA(cudaStreamWaitEvent(D.stream, D.ev_halo, 0));
+	}
+	if(D.n_offd_rows > 0)                                // z += a * A_offd * halo, boundary rows only
+		launch_gemv_add_rows(*D.offd, D.n_offd_rows, D.offd_rows, plain ? 1.0 : a, D.halo, z, D.stream);
 }
 
 struct DistOps : public KrylovOps {
@@ -190,8 +201,10 @@ struct DistOps : public KrylovOps {
 		if(nd > MAX_KRYLOV_DOTS) throw Error("dots: too many products");
 		for(int o = 0; o < nd; o += MAX_DOTS)
 			launch_multi_dot(n, std::min(MAX_DOTS, nd - o), a + o, b + o, partial, dout.p + o, stream);
-		if(D->comm->world > 1)
+		if(D->comm->world > 1) {
+			ProfScope ps(KC_ALLREDUCE, stream);
 			B200_NCCL(g_nccl.AllReduce(dout.p, dout.p, nd, ncclFloat64, ncclSum, D->comm->comm, stream));
+		}
 		return dout.p;
 	}
 	bool prec_reads_output() const override { return M && prec_sweeps_in_place(*M); }
@@ -256,7 +269,7 @@ int b200_dist_mat_create(b200_comm *comm, b200_mat *diag, b200_mat *offd, int nh
 {
 	return dguarded([&] {
 		if(!comm || !diag || !out) throw Error("null argument");
-		b200_dist_mat *h = new b200_dist_mat;
+		std::unique_ptr<b200_dist_mat> h(new b200_dist_mat);      // released to the caller on success
 		DistMat& D = h->d;
 		D.comm = &comm->c; D.diag = &diag->m; D.offd = offd ? &offd->m : nullptr;
 		D.bs = diag->m.bs; D.nhalo = nhalo; D.stream = diag->m.stream;
@@ -267,14 +280,19 @@ int b200_dist_mat_create(b200_comm *comm, b200_mat *diag, b200_mat *offd, int nh
 			D.recv_count.push_back(recv_counts[k]);
 			ns += send_counts[k]; nr += recv_counts[k];
 		}
-		if(nr != nhalo) { delete h; throw Error("halo plan: receive counts do not add up to nhalo"); }
+		if(nr != nhalo) throw Error("halo plan: receive counts do not add up to nhalo");
 		D.nsend = ns;
 		D.send_idx.alloc(std::max<long long>(ns, 1));
 		if(ns) B200_CUDA(cudaMemcpy(D.send_idx, send_idx, ns*sizeof(int), cudaMemcpyHostToDevice));
 		D.send_buf.alloc(std::max<long long>(ns*D.bs, 1));
 		D.halo.alloc(std::max<long long>((long long)nhalo*D.bs, 1));
 		B200_CUDA(cudaMemset(D.halo, 0, std::max<long long>((long long)nhalo*D.bs, 1)*sizeof(double)));
-		*out = h;
+		if(D.offd && D.offd->nnzb > 0) {
+			if(D.offd->nbrows != D.diag->nbrows || D.offd->bs != D.bs)
+				throw Error("halo plan: the coupling part must have the rows and block size of the diagonal part");
+			D.n_offd_rows = nonempty_rows(*D.offd, D.offd_rows, D.stream);
+		}
+		*out = h.release();
 	});
 }
 
@@ -283,6 +301,17 @@ void b200_dist_mat_destroy(b200_dist_mat *d) { delete d; }
 int b200_dist_mat_apply(b200_dist_mat *d, const double *d_x, double *d_y)
 {
 	return dguarded([&] { dist_spmv(d->d, 1.0, d_x, 0.0, nullptr, d_y, true); });
+}
+
+int b200_dist_mat_apply_with_halo(b200_dist_mat *d, const double *d_x, const double *d_halo, double *d_y)
+{
+	return dguarded([&] {
+		DistMat& D = d->d;
+		if(D.nhalo > 0 && !d_halo) throw Error("apply_with_halo: null halo");
+		launch_spmv(*D.diag, d_x, d_y, D.stream);
+		if(D.n_offd_rows > 0)
+			launch_gemv_add_rows(*D.offd, D.n_offd_rows, D.offd_rows, 1.0, d_halo, d_y, D.stream);
+	});
 }
 
 int b200_dist_solve(const char *solver, b200_dist_mat *A, b200_prec *M, const double *d_b,

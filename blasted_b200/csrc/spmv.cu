@@ -14,6 +14,8 @@
  *    x segment is a broadcast load, no shuffles are needed, the bs results are written contiguously.
  */
 #include "common.cuh"
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include "blockops.cuh"
 
 namespace b200 {
@@ -221,6 +223,82 @@ void launch_gemv3(const Mat& A, double a, const double *x, double b, const doubl
                   cudaStream_t st)
 {
 	dispatch<true>(A, a, x, b, y, z, st);
+}
+
+// z(rows) += a (A x)(rows) over a LIST of block rows: the coupling part of a partitioned operator
+// has entries in the subdomain's boundary rows only (2 of n planes of a z-slab), so the product
+// touches those rows instead of streaming the row pointers and z of the whole subdomain.
+
+template <int BS>
+__global__ void __launch_bounds__(256)
+rows_gemv_add_kernel(const int nlist, const int *__restrict__ rows, const int *__restrict__ browptr,
+                     const int *__restrict__ bcolind, const double *__restrict__ vals,
+                     const double *__restrict__ x, const double a, double *z)
+{
+	const long long tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	const long long idx = tid / BS;
+	const int r = (int)(tid - idx*BS);
+	if(idx >= nlist) return;
+	const int row = __ldg(rows + idx);
+	const int s = __ldg(browptr + row), e = __ldg(browptr + row + 1);
+	double acc = 0;
+	for(int jj = s; jj < e; jj++) {
+		const double *xc = x + (size_t)__ldg(bcolind + jj)*BS;
+		if(BS == 1) acc = fma(__ldg(vals + jj), __ldg(xc), acc);
+		else {
+			double av[BS];
+			BlkIO<BS>::template load_row<false>(vals + (size_t)jj*(BS*BS), r, av);
+#pragma unroll
+			for(int c = 0; c < BS; c++) acc = fma(av[c], __ldg(xc + c), acc);
+		}
+	}
+	z[(size_t)row*BS + r] += a*acc;
+}
+
+void launch_gemv_add_rows(const Mat& A, int nlist, const int *d_rows, double a, const double *x,
+                          double *z, cudaStream_t st)
+{
+	if(nlist == 0) return;
+	ProfScope ps(KC_SPMV, st);
+#define B200_ROWS_CASE(B)                                                                          \
+	case B: rows_gemv_add_kernel<B><<<div_up((long long)nlist*B, 256), 256, 0, st>>>(              \
+	            nlist, d_rows, A.browptr, A.bcolind, A.vals, x, a, z); break;
+	switch(A.bs) {
+	B200_ROWS_CASE(1) B200_ROWS_CASE(3) B200_ROWS_CASE(4) B200_ROWS_CASE(5) B200_ROWS_CASE(7)
+	default: throw Error("SpMV: block size " + std::to_string(A.bs) + " not supported");
+	}
+#undef B200_ROWS_CASE
+	B200_LAUNCHED();
+}
+
+__global__ void __launch_bounds__(256)
+nonempty_flags_kernel(const int n, const int *__restrict__ browptr, char *__restrict__ flag)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i < n) flag[i] = browptr[i+1] > browptr[i];
+}
+
+int nonempty_rows(const Mat& A, DevBuf<int>& rows, cudaStream_t st)
+{
+	const int n = A.nbrows;
+	if(n == 0 || A.nnzb == 0) return 0;
+	DevBuf<char> flag, tmp;
+	DevBuf<int> d_cnt, all;
+	flag.alloc(n); d_cnt.alloc(1); all.alloc(n);
+	nonempty_flags_kernel<<<div_up(n, 256), 256, 0, st>>>(n, A.browptr, flag);
+	B200_LAUNCHED();
+	size_t tb = 0;
+	thrust::counting_iterator<int> ids(0);
+	cub::DeviceSelect::Flagged(nullptr, tb, ids, flag.p, all.p, d_cnt.p, n, st);
+	tmp.alloc(tb);
+	B200_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids, flag.p, all.p, d_cnt.p, n, st));
+	int cnt = 0;
+	B200_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	rows.alloc(std::max(cnt, 1));
+	B200_CUDA(cudaMemcpyAsync(rows, all, (size_t)cnt*sizeof(int), cudaMemcpyDeviceToDevice, st));
+	B200_CUDA(cudaStreamSynchronize(st));
+	return cnt;
 }
 
 }  // namespace b200

@@ -273,6 +273,16 @@ class DistMatrix:
         check(lib.b200_dist_mat_apply(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr())))
         return y
 
+    def apply_with_halo(self, x, halo, y=None):
+        """y_local = A_diag x + A_offd halo with a halo buffer the caller filled (plan order).  Not
+        collective: no exchange is posted."""
+        import torch
+        y = torch.empty_like(x) if y is None else y
+        hp = C.c_void_p(halo.data_ptr()) if halo is not None and halo.numel() else None
+        check(lib.b200_dist_mat_apply_with_halo(self._h, C.c_void_p(x.data_ptr()), hp,
+                                                C.c_void_p(y.data_ptr())))
+        return y
+
     def solve(self, solver: str, prec: Optional[Preconditioner], b, x, tol=1e-8, maxiter=1000,
               restart=30) -> SolveInfo:
         """Distributed Krylov solve with the local (block-Jacobi) preconditioner.  Collective."""

@@ -456,6 +456,9 @@ class FGMRES(GCR):
 # ---- per-kernel-class device timing (b200_profile_*) ----
 KERNEL_CLASSES = ["factor_lower", "factor_upper", "factor_init", "diag_invert", "tri_lower",
                   "tri_upper", "spmv", "other"]
+# Krylov drivers and the partitioned layer: BLAS-1 launches, halo pack, time the compute stream
+# waited for the halo, all-reduce of the dot products (includes waiting for the slowest rank)
+ALL_CLASSES = KERNEL_CLASSES + ["blas1", "halo_pack", "halo_wait", "allreduce"]
 
 
 def profile_enable(on: bool = True) -> None:
@@ -472,3 +475,13 @@ def profile_get():
     cnt = np.zeros(8, dtype=np.int64)
     check(lib.b200_profile_get(ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
     return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+
+def profile_get_all():
+    """profile_get() over every class (ALL_CLASSES)."""
+    n = lib.b200_profile_classes()
+    assert n == len(ALL_CLASSES)
+    ms = np.zeros(n)
+    cnt = np.zeros(n, dtype=np.int64)
+    check(lib.b200_profile_get_n(n, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(ALL_CLASSES)}

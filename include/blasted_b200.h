@@ -97,6 +97,11 @@ void b200_reset_kernel_launches(void);
 void b200_profile_enable(int on);
 void b200_profile_reset(void);
 int b200_profile_get(double ms[8], long long count[8]);
+/* All classes: the eight above, then 8 BLAS-1 of the Krylov drivers (dots, axpys), 9 halo pack,
+ * 10 time the compute stream waited for the halo, 11 all-reduce of the dot products (includes the
+ * wait for the slowest rank).  n <= b200_profile_classes(). */
+int b200_profile_classes(void);
+int b200_profile_get_n(int n, double *ms, long long *count);
 
 /* ---- device-resident matrix: SRMatrixStorage + CSRMatrixView/BSRMatrixView
  *      (include/srmatrixdefs.hpp:38-79, include/blockmatrices.hpp:71-160) ---- */
@@ -288,6 +293,10 @@ int b200_dist_mat_create(b200_comm *comm, b200_mat *diag, b200_mat *offd, int nh
 void b200_dist_mat_destroy(b200_dist_mat *d);
 /** y_local = (A x)_local with halo exchange (device pointers, collective over the communicator). */
 int b200_dist_mat_apply(b200_dist_mat *d, const double *d_x, double *d_y);
+/** The same product with a halo the CALLER has filled (nhalo*bs values in the plan's receive order,
+ *  e.g. by a PETSc VecScatter): y = A_diag x + A_offd halo.  Not collective, no NCCL; the coupling
+ *  part touches the subdomain's boundary rows only. */
+int b200_dist_mat_apply_with_halo(b200_dist_mat *d, const double *d_x, const double *d_halo, double *d_y);
 /** The Krylov drivers of b200_solve on the partitioned operator; M is the local (block-Jacobi)
  *  preconditioner of `diag`.  Collective.  info->iters etc. are identical on every rank. */
 int b200_dist_solve(const char *solver, b200_dist_mat *A, b200_prec *M, const double *d_b,

@@ -132,3 +132,77 @@ def test_slab_device_solve_matches_host_assembled():
         assert info.converged and float((x - 1).abs().max()) < 1e-7
         runs.append(info.iters)
     assert runs[0] == runs[1]
+
+
+def test_profile_classes_of_a_partitioned_solve():
+    """b200_profile_get_n: the Krylov and exchange classes are counted next to the kernel classes
+    (what bench.py's per-iteration breakdown reads); the first eight agree with b200_profile_get."""
+    import torch
+    import blasted_b200 as bb
+    from blasted_b200 import solverfactory as sf
+    from blasted_b200.dist import Comm, DistMatrix, poisson3d_slab_device
+    part, view = poisson3d_slab_device(16, 0, 1)
+    A = DistMatrix(Comm.single(), part, view)
+    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=2, napplysweeps=2)
+    prec = bb.SRFactory().create_preconditioner(A.diag, s)
+    prec.compute()
+    b = A.apply(torch.ones(A.local_dim(), dtype=torch.float64, device="cuda"))
+    x = torch.zeros_like(b)
+    sf.profile_reset()
+    sf.profile_enable(True)
+    try:
+        info = A.solve("fgmres", prec, b, x, tol=1e-8, maxiter=200, restart=30)
+    finally:
+        sf.profile_enable(False)
+    assert info.converged
+    every, basic = sf.profile_get_all(), sf.profile_get()
+    for k in sf.KERNEL_CLASSES:
+        assert every[k] == basic[k]
+    assert every["blas1"][1] >= 3*info.iters and every["blas1"][0] > 0
+    assert every["spmv"][1] >= info.iters
+    assert every["tri_lower"][1] >= 2*info.iters
+    assert every["allreduce"][1] == 0 and every["halo_wait"][1] == 0     # one subdomain: no exchange
+    sf.profile_reset()
+    assert all(v == (0.0, 0) for v in sf.profile_get_all().values())
+
+
+@pytest.mark.parametrize("mk", [lambda m: m.poisson3d(0, 7, dims=(9, 7, 11)),
+                                lambda m: m.poisson3d(0, 27, dims=(6, 5, 8)),
+                                lambda m: m.block_stencil((13, 11), 3, 5),
+                                lambda m: m.block_stencil((12, 10), 4, 6),
+                                lambda m: m.block_stencil((7, 6, 5), 5, 7),
+                                lambda m: m.block_stencil((6, 5), 7, 8)])
+@pytest.mark.parametrize("nparts", [2, 3, 5])
+def test_partitioned_product_with_caller_filled_halo(mk, nparts):
+    """Every rank's share of a P-way partitioned product on ONE GPU: the halo is filled by the test
+    from the plan's send lists (which also checks that send and receive orders agree), the coupling
+    part runs over the boundary rows only (`rows_gemv_add_kernel`).  Reference product:
+    src/kernels/matvecs.cpp:78-108 on the whole matrix."""
+    import torch
+    from blasted_b200 import matgen
+    from blasted_b200.dist import Comm, DistMatrix, partition_rows
+    from oracle import orc
+    m = mk(matgen)
+    bs = m.bs
+    x = np.random.default_rng(11).standard_normal(m.dim)
+    want = orc().spmv(m, x)
+    parts = partition_rows(m, nparts)
+    comm = Comm.single()
+    for p in parts:
+        # what each neighbour q sends to p, in p's receive order
+        segs = []
+        for q in p.neigh:
+            pq = parts[q]
+            k = pq.neigh.index(p.rank)
+            o = int(np.sum(pq.send_counts[:k]))
+            rows = pq.send_idx[o:o + pq.send_counts[k]].astype(np.int64) + pq.row_begin
+            assert len(rows) == p.recv_counts[p.neigh.index(q)]
+            segs.append((rows[:, None]*bs + np.arange(bs)[None, :]).reshape(-1))
+        halo = x[np.concatenate(segs)] if segs else np.zeros(0)
+        assert len(halo) == p.nhalo*bs
+        A = DistMatrix(comm, p)
+        xl = torch.from_numpy(x[p.row_begin*bs:p.row_end*bs].copy()).cuda()
+        y = A.apply_with_halo(xl, torch.from_numpy(halo.copy()).cuda()).cpu().numpy()
+        ref = want[p.row_begin*bs:p.row_end*bs]
+        assert np.abs(y - ref).max() <= 1e-13*np.abs(want).max()
+        A.close()
