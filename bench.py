@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 
 SEED = 20261018 + 2
 NBUILD, NAPPLY = 3, 3
+FGMRES_SWEEPS = (5, 3)      # fastest of tools/solve_study512.py (profiles/solve_study512_r02.log)
 
 
 # ----------------------------------------------------------------------------- workload + bytes
@@ -509,8 +510,8 @@ def run_configs(peak):
 
 def run_fgmres(n, rank, world, dist, reps=1):
     """Time to solve A x = b (7-point Poisson n^3, x* = 1) to rel. residual 1e-8 with FGMRES(30)
-    preconditioned by per-subdomain async ILU(0) (5 build sweeps, 5 apply sweep pairs; measured
-    fastest in tools/solve_study.py).  The operator is assembled on the device (z-slab per rank,
+    preconditioned by per-subdomain async ILU(0) (FGMRES_SWEEPS build sweeps / apply sweep pairs;
+    measured fastest in tools/solve_study512.py).  The operator is assembled on the device (z-slab per rank,
     generator of tests/poisson3d-fd/poisson3d_fd.cpp:108-139 on a uniform grid)."""
     import torch
     import blasted_b200 as bb
@@ -521,7 +522,8 @@ def run_fgmres(n, rank, world, dist, reps=1):
     t_setup = time.perf_counter()
     part, diag_view = poisson3d_slab_device(n, rank, world)
     A = DistMatrix(comm, part, diag_view)
-    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=5, napplysweeps=5)
+    s = bb.AsyncSolverSettings(prectype=sf.SOLVER_TYPES["ilu0"], bs=1, nbuildsweeps=FGMRES_SWEEPS[0],
+                               napplysweeps=FGMRES_SWEEPS[1])
     prec = bb.SRFactory().create_preconditioner(A.diag, s)
     nloc = A.local_dim()
     ones = torch.ones(nloc, dtype=torch.float64, device="cuda")
@@ -585,7 +587,8 @@ def run_fgmres(n, rank, world, dist, reps=1):
     mem = torch.cuda.max_memory_allocated()/2**30
     free, total = torch.cuda.mem_get_info()
     return {"problem": f"7-point Poisson {n}^3, z-slabs over {world} GPU(s), block-Jacobi async ILU(0) "
-                       "(5,5) + FGMRES(30), rel. tol 1e-8", "scaling": "strong",
+                       f"({FGMRES_SWEEPS[0]},{FGMRES_SWEEPS[1]}) + FGMRES(30), rel. tol 1e-8",
+            "scaling": "strong", "sweeps": list(FGMRES_SWEEPS),
             "unknowns": n**3, "iterations": info.iters, "converged": bool(info.converged),
             "time_to_solve_ms": best, "ms_per_iteration": best/max(info.iters, 1),
             "factor_included": True, "max_abs_error": float(errt.item()),

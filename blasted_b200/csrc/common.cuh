@@ -255,6 +255,8 @@ struct StreamArgs {
 	double alpha = 1, beta = 0;
 	int row_begin = 0, row_end = 0;
 	int descending = 0;
+	const double *xscale = nullptr;   ///< sweeps: the gathered vector is x .* xscale
+	int chain = 0;           ///< asynchronous sweeps: rows of a warp solved exactly along i -> i±1
 };
 bool stream_supported(int max_row_len);
 void launch_csr_stream(StreamKind kind, const StreamArgs& a, int max_len, cudaStream_t st);
@@ -397,6 +399,8 @@ struct Prec {
 	void *level_graph[2] = {nullptr, nullptr};        ///< cudaGraphExec_t
 	DevBuf<int> sync_flags;                           ///< {ticket, error} of the one-launch exact solves
 	DevBuf<int> rowdone;                              ///< per-row flags of the one-launch exact factorisation
+	/// asynchronous scalar sweeps solve the rows of a warp exactly along i -> i±1 (csrstream.cu)
+	bool chain_sweeps = getenv("B200_NO_CHAIN") == nullptr;          // A/B switch (development)
 	int a_max_lower = 0, a_max_upper = 0;             ///< longest row parts of A (block SGS sweeps)
 	DevBuf<int> exact_slots;                          ///< blocks: level-sorted rows, levels padded to whole warps
 	int n_exact_slots = 0;

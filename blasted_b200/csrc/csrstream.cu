@@ -25,7 +25,7 @@ namespace b200 {
 
 constexpr int STREAM_CAP = 3584;       // entries staged per CTA: 28 KiB of values + 14 KiB of indices
 
-template <int KIND, int LPR, int RPT, int CAP>
+template <int KIND, int LPR, int RPT, int CAP, bool CHAIN>
 __global__ void __launch_bounds__(256)
 csr_stream_kernel(const StreamArgs a)
 {
@@ -82,33 +82,83 @@ csr_stream_kernel(const StreamArgs a)
 	const double *tv = sval + (e0 - v0) - e0;       // tv[e] = value of entry e
 	const int *tc = scol + (e0 - c0) - e0;
 
-	// rows: gather, multiply, add, single final store per row
+	// what a row's new value is, given the sum over its stored entries
+	auto finish = [&](const int k, const int row, const double sum) -> double {
+		if(KIND == STREAM_SPMV) return sum;
+		else if(KIND == STREAM_GEMV3) return a.alpha*sum + rhs[k];
+		else if(KIND == STREAM_TRI_LOWER) return rhs[k] - sum;
+		else if(KIND == STREAM_TRI_UPPER) return (1.0/__ldg(a.diag + row))*(rhs[k] - sum);
+		else if(KIND == STREAM_SGS_FWD) return __ldg(a.diag + row)*(rhs[k] - sum);   // diag = 1/a_ii
+		else return rhs[k] - __ldg(a.diag + row)*sum;                               // STREAM_SGS_BWD
+	};
+
+	// rows: gather, multiply, add, single final store per row.  A thread's row groups are taken in
+	// sweep direction and each is stored before the next is gathered: how early a new value
+	// becomes visible to the other CTAs decides how many sweeps a solve needs (7-point 512^3,
+	// FGMRES(30), sweeps (5,3): 2631 iterations this way, 3435 with the stores after both groups).
+	constexpr bool FORWARD = (KIND == STREAM_TRI_LOWER || KIND == STREAM_SGS_FWD);
+	constexpr bool BACKWARD = (KIND == STREAM_TRI_UPPER || KIND == STREAM_SGS_BWD);
 #pragma unroll
-	for(int k = 0; k < RPT; k++) {
+	for(int kk = 0; kk < RPT; kk++) {
+		const int k = BACKWARD ? RPT - 1 - kk : kk;
 		const int lr = (LPR > 1) ? tid/LPR : tid + k*256;
 		const int lane = (LPR > 1) ? tid - lr*LPR : 0;
-		double sum = 0;
+		const int w = tid & 31;
+		double sum = 0, chain = 0;
 		if(lr < nr) {
 			const int s = sptr[lr], e = sptr[lr + 1];
+			// CHAIN: the entry that couples the row to its neighbour in sweep direction is kept
+			// apart when that neighbour belongs to the adjacent lane of this warp
+			const int nb = !CHAIN ? -1 : FORWARD ? (w > 0 ? r0 + lr - 1 : -1)
+			                                     : ((w < 31 && lr + 1 < nr) ? r0 + lr + 1 : -1);
 #pragma unroll 4
 			for(int i = s + lane; i < e; i += LPR) {
 				const int c = tc[i];
-				const double xv = (KIND == STREAM_SPMV || KIND == STREAM_GEMV3) ? __ldg(a.x + c)
-				                                                               : __ldcg(a.x + c);
-				sum = fma(tv[i], xv, sum);
+				double xv = (KIND == STREAM_SPMV || KIND == STREAM_GEMV3) ? __ldg(a.x + c)
+				                                                         : __ldcg(a.x + c);
+				if(KIND != STREAM_SPMV && KIND != STREAM_GEMV3 && a.xscale) xv *= __ldg(a.xscale + c);
+				double v = tv[i];
+				if(CHAIN) {                      // branch-free: the chain entry leaves the sum
+					const bool is = (c == nb);
+					chain = is ? v : chain;
+					v = is ? 0.0 : v;
+				}
+				sum = fma(v, xv, sum);
 			}
 		}
 #pragma unroll
 		for(int off = LPR/2; off > 0; off >>= 1)
 			sum += __shfl_down_sync(0xffffffffu, sum, off, LPR);
-		if(lr < nr && lane == 0) {
-			const int row = r0 + lr;
-			if(KIND == STREAM_SPMV) a.out[row] = sum;
-			else if(KIND == STREAM_GEMV3) a.out[row] = a.alpha*sum + rhs[k];
-			else if(KIND == STREAM_TRI_LOWER) a.out[row] = rhs[k] - sum;
-			else if(KIND == STREAM_TRI_UPPER) a.out[row] = (1.0/__ldg(a.diag + row))*(rhs[k] - sum);
-			else if(KIND == STREAM_SGS_FWD) a.out[row] = __ldg(a.diag + row)*(rhs[k] - sum);   // diag = 1/a_ii
-			else a.out[row] = rhs[k] - __ldg(a.diag + row)*sum;                               // STREAM_SGS_BWD
+		if(!CHAIN) {
+			if(lr < nr && lane == 0) a.out[r0 + lr] = finish(k, r0 + lr, sum);
+		}
+		else {
+			// The 32 consecutive rows of a warp are solved EXACTLY along that chain, as a thread
+			// of the reference does for the rows of its chunk (kernels_ilu_apply.hpp:15-42 under
+			// schedule(dynamic, chunk): rows in order, the predecessor's new value is used): the
+			// new values obey v_i = A_i v_(i±1) + C_i, a first-order recurrence, evaluated by a
+			// warp scan over the affine maps (5 steps).  Everything else stays a relaxed read.
+			double C = 0, A = 0;
+			if(lr < nr) {
+				const int row = r0 + lr;
+				if(KIND == STREAM_TRI_LOWER) { C = rhs[k] - sum; A = -chain; }
+				else if(KIND == STREAM_TRI_UPPER) {
+					const double dinv = 1.0/__ldg(a.diag + row);
+					C = dinv*(rhs[k] - sum); A = -chain*dinv;
+				}
+				else {
+					const double d = __ldg(a.diag + row);            // 1/a_ii
+					C = (KIND == STREAM_SGS_FWD) ? d*(rhs[k] - sum) : rhs[k] - d*sum;
+					A = -chain*d;
+				}
+			}
+#pragma unroll
+			for(int off = 1; off < 32; off <<= 1) {
+				const double Ao = FORWARD ? __shfl_up_sync(0xffffffffu, A, off) : __shfl_down_sync(0xffffffffu, A, off);
+				const double Co = FORWARD ? __shfl_up_sync(0xffffffffu, C, off) : __shfl_down_sync(0xffffffffu, C, off);
+				if(FORWARD ? (w >= off) : (w + off < 32)) { C = fma(A, Co, C); A *= Ao; }
+			}
+			if(lr < nr) a.out[r0 + lr] = C;
 		}
 	}
 }
@@ -122,12 +172,19 @@ static void launch_kind(const StreamArgs& a, int max_len, cudaStream_t st)
 	// (more resident CTAs, staging and row phases of different CTAs overlap) for the short row
 	// parts of the triangular sweeps; the largest tiles for full rows.
 	static const bool small = getenv("B200_STREAM_LARGE") == nullptr;
+	constexpr bool tri = (KIND != STREAM_SPMV && KIND != STREAM_GEMV3);
 #define B200_STREAM_CASE(L, P, C)                                                  \
 	{                                                                              \
 		constexpr int R = 256*P/L;                                                 \
-		csr_stream_kernel<KIND,L,P,C><<<div_up(nrows, R), 256, 0, st>>>(a);        \
+		bool done = false;                                                         \
+		if constexpr(tri && L == 1) {                                              \
+			if(a.chain) {                                                          \
+				csr_stream_kernel<KIND,L,P,C,true><<<div_up(nrows, R), 256, 0, st>>>(a); \
+				done = true;                                                       \
+			}                                                                      \
+		}                                                                          \
+		if(!done) csr_stream_kernel<KIND,L,P,C,false><<<div_up(nrows, R), 256, 0, st>>>(a); \
 	}
-	const bool tri = (KIND != STREAM_SPMV && KIND != STREAM_GEMV3);
 	if(tri && small && max_len <= 3) B200_STREAM_CASE(1, 2, 1536)
 	else if(tri && small && max_len <= 7) B200_STREAM_CASE(1, 1, 1792)
 	else if(max_len <= STREAM_CAP/1024) B200_STREAM_CASE(1, 4, STREAM_CAP)

@@ -422,7 +422,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 		StreamArgs sa;
 		if(split) {
 			sa.ptr = P.pl.lptr; sa.col = P.pl.lcol; sa.val = P.sf.lval; sa.x = P.ytemp; sa.out = P.ytemp;
-			sa.rhs = r; sa.diag = P.dinv; sa.row_end = A.nbrows;
+			sa.rhs = r; sa.diag = P.dinv; sa.row_end = A.nbrows; sa.chain = P.chain_sweeps;
 		}
 		for(int sw = 0; sw < P.s.napplysweeps; sw++) {
 			if(split) {
@@ -443,6 +443,7 @@ void prec_apply(Prec& P, const double *r, double *z)
 			sa = StreamArgs();
 			sa.ptr = P.pl.uptr; sa.col = P.pl.ucol; sa.val = P.sf.uval; sa.x = z; sa.out = z;
 			sa.rhs = P.ytemp; sa.diag = P.dinv; sa.row_end = A.nbrows; sa.descending = 1;
+			sa.chain = P.chain_sweeps;
 		}
 		for(int sw = 0; sw < P.s.napplysweeps; sw++) {
 			if(split) {
@@ -499,20 +500,30 @@ void prec_apply(Prec& P, const double *r, double *z)
 			// z := S r is folded into the L sweep (rhs scaled on the fly).
 			const int ai = P.s.apply_inittype;
 			if(ai == B200_INIT_A_NONE) throw Error(" scalar_ilu0_apply: Invalid init type!");
-			B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
+			// The first two lower sweeps are ONE pass: from y = 0 the first gives y = S r, so the
+			// second gathers S r itself (no memset, one pass over L less); likewise the first upper
+			// sweep gathers its initial guess z = y from ytemp instead of from a copy.
+			static const bool fuse_env = getenv("B200_NO_FUSE_FIRST") == nullptr;   // A/B switch
+			const bool fuse = fuse_env && stream && P.s.napplysweeps >= 2;
+			if(!fuse) B200_CUDA(cudaMemsetAsync(P.ytemp, 0, n*sizeof(double), st));
 			aL.rhs = r; aL.rscale = scale; aL.x = P.ytemp; aL.descending = false;
 			StreamArgs sa;
 			if(stream) {
 				sa.ptr = P.pl.lptr; sa.col = P.pl.lcol; sa.val = P.sf.lval; sa.x = P.ytemp;
 				sa.out = P.ytemp; sa.rhs = r; sa.rscale = scale; sa.row_end = A.nbrows;
+				sa.chain = P.chain_sweeps;
 			}
-			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
+			for(int sw = fuse ? 1 : 0; sw < P.s.napplysweeps; sw++) {
 				if(stream) {
 					ProfScope ps(KC_TRI_LOWER, st);
+					sa.x = (fuse && sw == 1) ? r : P.ytemp;
+					sa.xscale = (fuse && sw == 1) ? scale : nullptr;
 					launch_csr_stream(STREAM_TRI_LOWER, sa, std::max(P.pl.max_lower_len, 1), st);
 				} else launch_tri_sweep(A, TRI_ILU_LOWER, aL, st);
 			}
-			if(ai == B200_INIT_A_JACOBI)
+			const bool fuse_u = fuse && ai == B200_INIT_A_JACOBI;
+			if(fuse_u) {}
+			else if(ai == B200_INIT_A_JACOBI)
 				B200_CUDA(cudaMemcpyAsync(z, P.ytemp, n*sizeof(double), cudaMemcpyDeviceToDevice, st));
 			else
 				B200_CUDA(cudaMemsetAsync(z, 0, n*sizeof(double), st));
@@ -521,10 +532,12 @@ void prec_apply(Prec& P, const double *r, double *z)
 				sa = StreamArgs();
 				sa.ptr = P.pl.uptr; sa.col = P.pl.ucol; sa.val = P.sf.uval; sa.x = z; sa.out = z;
 				sa.rhs = P.ytemp; sa.diag = P.sf.udiag; sa.row_end = A.nbrows; sa.descending = 1;
+				sa.chain = P.chain_sweeps;
 			}
 			for(int sw = 0; sw < P.s.napplysweeps; sw++) {
 				if(stream) {
 					ProfScope ps(KC_TRI_UPPER, st);
+					sa.x = (fuse_u && sw == 0) ? P.ytemp.p : z;
 					launch_csr_stream(STREAM_TRI_UPPER, sa, std::max(P.pl.max_upper_len, 1), st);
 				} else launch_tri_sweep(A, TRI_ILU_UPPER, aU, st);
 			}

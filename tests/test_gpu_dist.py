@@ -160,7 +160,8 @@ def test_profile_classes_of_a_partitioned_solve():
         assert every[k] == basic[k]
     assert every["blas1"][1] >= 3*info.iters and every["blas1"][0] > 0
     assert every["spmv"][1] >= info.iters
-    assert every["tri_lower"][1] >= 2*info.iters
+    assert every["tri_lower"][1] >= info.iters            # two lower sweeps are ONE pass (first two fused)
+    assert every["tri_upper"][1] >= 2*info.iters
     assert every["allreduce"][1] == 0 and every["halo_wait"][1] == 0     # one subdomain: no exchange
     sf.profile_reset()
     assert all(v == (0.0, 0) for v in sf.profile_get_all().values())
